@@ -1,0 +1,641 @@
+// FLAME head decoder for sm_100a:  413 params -> 5023x3 vertices (+ weak-perspective projection) in three kernels
+//   K1 flame_prep_kernel    per-head small math: betas -> fp16 hi/lo coefficient rows, folded joint regression,
+//                           Rodrigues, kinematic chain, 6-DoF rotation folded into the skinning transforms
+//   K2 tile_gemm_kernel<EpiBlend>   blend shapes + pose correctives as ONE tcgen05 GEMM  [heads,448] x [15069,448]^T
+//   K3 lbs_project_kernel   linear-blend skinning + z offset + rotation + projection, shared-memory staged, coalesced
+//   K4 gather kernels       landmark subsets
+// Reference math: model_training/model/flame.py:182-229, smplx.lbs (0.1.26), model_training/model/utils.py:92-101,
+// model_training/head_mesh.py:33-46.  See DESIGN.md for layouts and rooflines.
+#include <cuda_fp16.h>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "../../include/dad3d.h"
+#include "common.h"
+#include "tile_gemm.cuh"
+#include "tmap.h"
+
+namespace dad3d {
+
+constexpr int kJoints = 5;
+constexpr int kMaxShape = 300;        // flame.py:107
+constexpr int kMaxExpr = 100;         // flame.py:108
+constexpr int kBetas = kMaxShape + kMaxExpr;
+constexpr int kPoseFeat = (kJoints - 1) * 9;
+constexpr int kKPad = 448;            // 400 betas + 36 pose features, padded to 7 x 64
+constexpr int kXfFloats = 68;         // per-head transform record (see HeadXf layout below)
+constexpr int kBlendBlockN = 128;
+constexpr int kDecodeChunk = 4096;    // heads per internal pass (bounds the v_posed scratch to ~250 MB)
+constexpr float kMeshOffsetZ = 0.05f; // flame.py:114
+
+struct FlameLayoutDev {
+  int n_params;
+  int off_shape, n_shape, off_expr, n_expr, off_jaw, n_jaw, off_rot, off_eye, n_eye, off_neck, n_neck, off_trans,
+      off_scale;
+  int parents[kJoints];
+};
+
+// HeadXf record (68 floats): A[j][12] for j<5 (rows of [R | t], already left-multiplied by the 6-DoF rotation),
+// then c[3] = R6 * (0,0,0.05), then sc = max(s+1,1e-8), tx, ty, 2 pad.
+
+// ------------------------------------------------------------------------------------------------ K1
+__device__ __forceinline__ void rodrigues(const float* r, float* R) {
+  // smplx batch_rodrigues: the epsilon is added to the vector inside the norm
+  const float ax = r[0] + 1e-8f, ay = r[1] + 1e-8f, az = r[2] + 1e-8f;
+  const float angle = sqrtf(ax * ax + ay * ay + az * az);
+  const float x = r[0] / angle, y = r[1] / angle, z = r[2] / angle;
+  const float s = sinf(angle), c1 = 1.0f - cosf(angle);
+  // K = [[0,-z,y],[z,0,-x],[-y,x,0]],  R = I + s K + (1-c) K K
+  R[0] = 1.0f + c1 * (-(z * z) - y * y);
+  R[1] = s * (-z) + c1 * (x * y);
+  R[2] = s * (y) + c1 * (x * z);
+  R[3] = s * (z) + c1 * (x * y);
+  R[4] = 1.0f + c1 * (-(z * z) - x * x);
+  R[5] = s * (-x) + c1 * (y * z);
+  R[6] = s * (-y) + c1 * (x * z);
+  R[7] = s * (x) + c1 * (y * z);
+  R[8] = 1.0f + c1 * (-(y * y) - x * x);
+}
+
+__device__ __forceinline__ void mat3_mul(const float* A, const float* B, float* C) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+}
+__device__ __forceinline__ void mat3_vec(const float* A, const float* v, float* o) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) o[i] = A[3 * i] * v[0] + A[3 * i + 1] * v[1] + A[3 * i + 2] * v[2];
+}
+
+__device__ __forceinline__ void split_store(__half* hi, __half* lo, size_t idx, float x) {
+  const __half h = __float2half_rn(x);
+  hi[idx] = h;
+  lo[idx] = __float2half_rn(x - __half2float(h));
+}
+
+__global__ void __launch_bounds__(256)
+flame_prep_kernel(const float* __restrict__ params, int B, FlameLayoutDev L, const float* __restrict__ jt,
+                  const float* __restrict__ jdirsT, int flags, __half* __restrict__ a_hi, __half* __restrict__ a_lo,
+                  float* __restrict__ xf) {
+  const int h = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (h >= B) return;
+  const float* p = params + static_cast<size_t>(h) * L.n_params;
+  const size_t arow = static_cast<size_t>(h) * kKPad;
+
+  float acc[15];
+#pragma unroll
+  for (int j = 0; j < 15; ++j) acc[j] = 0.f;
+  for (int l = lane; l < kBetas; l += 32) {
+    float b = 0.f;                                   // flame.py:191-200: missing coefficients are registered zeros
+    if (l < kMaxShape) {
+      if (l < L.n_shape) b = p[L.off_shape + l];
+    } else if (l - kMaxShape < L.n_expr) {
+      b = p[L.off_expr + l - kMaxShape];
+    }
+    split_store(a_hi, a_lo, arow + l, b);
+#pragma unroll
+    for (int j = 0; j < 15; ++j) acc[j] = fmaf(b, __ldg(&jdirsT[j * kBetas + l]), acc[j]);
+  }
+  for (int l = kBetas + kPoseFeat + lane; l < kKPad; l += 32) {
+    a_hi[arow + l] = __float2half_rn(0.f);
+    a_lo[arow + l] = __float2half_rn(0.f);
+  }
+#pragma unroll
+  for (int j = 0; j < 15; ++j) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+  }
+  if (lane != 0) return;
+
+  float J[15];
+#pragma unroll
+  for (int j = 0; j < 15; ++j) J[j] = __ldg(&jt[j]) + acc[j];       // joints = J_regressor (T + S beta), folded
+
+  // full_pose = [global 0, neck, jaw, eyeballs]   flame.py:201-208
+  float pose[15];
+#pragma unroll
+  for (int j = 0; j < 15; ++j) pose[j] = 0.f;
+  if (L.n_neck == 3)
+    for (int k = 0; k < 3; ++k) pose[3 + k] = p[L.off_neck + k];
+  if (L.n_jaw == 3 && !(flags & DAD3D_ZERO_JAW))
+    for (int k = 0; k < 3; ++k) pose[6 + k] = p[L.off_jaw + k];
+  if (L.n_eye == 6)
+    for (int k = 0; k < 6; ++k) pose[9 + k] = p[L.off_eye + k];
+
+  float R[kJoints][9];
+  for (int j = 0; j < kJoints; ++j) rodrigues(&pose[3 * j], R[j]);
+  for (int j = 1; j < kJoints; ++j)
+    for (int e = 0; e < 9; ++e) {
+      const float pf = R[j][e] - ((e == 0 || e == 4 || e == 8) ? 1.0f : 0.0f);
+      split_store(a_hi, a_lo, arow + kBetas + (j - 1) * 9 + e, pf);
+    }
+
+  // kinematic chain (smplx batch_rigid_transform)
+  float GR[kJoints][9], Gt[kJoints][3];
+  for (int e = 0; e < 9; ++e) GR[0][e] = R[0][e];
+  for (int k = 0; k < 3; ++k) Gt[0][k] = J[k];
+  for (int i = 1; i < kJoints; ++i) {
+    const int par = L.parents[i];
+    float rel[3], tmp[3];
+    for (int k = 0; k < 3; ++k) rel[k] = J[3 * i + k] - J[3 * par + k];
+    mat3_mul(GR[par], R[i], GR[i]);
+    mat3_vec(GR[par], rel, tmp);
+    for (int k = 0; k < 3; ++k) Gt[i][k] = tmp[k] + Gt[par][k];
+  }
+
+  // 6-DoF rotation (model/utils.py:92-101): columns b1, b2, b3
+  float R6[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  if (!(flags & DAD3D_ZERO_ROT)) {
+    const float* r6 = p + L.off_rot;
+    const float vx[3] = {r6[0], r6[1], r6[2]}, vy[3] = {r6[3], r6[4], r6[5]};
+    const float n1 = fmaxf(sqrtf(vx[0] * vx[0] + vx[1] * vx[1] + vx[2] * vx[2]), 1e-12f);
+    const float b1[3] = {vx[0] / n1, vx[1] / n1, vx[2] / n1};
+    float c3[3] = {b1[1] * vy[2] - b1[2] * vy[1], b1[2] * vy[0] - b1[0] * vy[2], b1[0] * vy[1] - b1[1] * vy[0]};
+    const float n3 = fmaxf(sqrtf(c3[0] * c3[0] + c3[1] * c3[1] + c3[2] * c3[2]), 1e-12f);
+    const float b3[3] = {c3[0] / n3, c3[1] / n3, c3[2] / n3};
+    const float b2[3] = {-(b1[1] * b3[2] - b1[2] * b3[1]), -(b1[2] * b3[0] - b1[0] * b3[2]),
+                         -(b1[0] * b3[1] - b1[1] * b3[0])};
+    for (int r = 0; r < 3; ++r) {
+      R6[3 * r + 0] = b1[r];
+      R6[3 * r + 1] = b2[r];
+      R6[3 * r + 2] = b3[r];
+    }
+  }
+
+  float* o = xf + static_cast<size_t>(h) * kXfFloats;
+  for (int i = 0; i < kJoints; ++i) {
+    float t[3], rj[3], AR[9], At[3];
+    mat3_vec(GR[i], &J[3 * i], rj);                     // rotated rest joint
+    for (int k = 0; k < 3; ++k) t[k] = Gt[i][k] - rj[k];
+    mat3_mul(R6, GR[i], AR);
+    mat3_vec(R6, t, At);
+    for (int r = 0; r < 3; ++r) {
+      o[i * 12 + r * 4 + 0] = AR[3 * r + 0];
+      o[i * 12 + r * 4 + 1] = AR[3 * r + 1];
+      o[i * 12 + r * 4 + 2] = AR[3 * r + 2];
+      o[i * 12 + r * 4 + 3] = At[r];
+    }
+  }
+  for (int r = 0; r < 3; ++r) o[60 + r] = R6[3 * r + 2] * kMeshOffsetZ;   // R6 * (0,0,0.05)   flame.py:224
+  o[63] = fmaxf(p[L.off_scale] + 1.0f, 1e-8f);                            // head_mesh.py:39
+  o[64] = p[L.off_trans + 0];                                             // head_mesh.py:41-42 (z is zeroed)
+  o[65] = p[L.off_trans + 1];
+  o[66] = 0.f;
+  o[67] = 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------ K2 epilogue
+struct EpiBlend {
+  struct Params {
+    float* out;          // [rows, ld] fp32 v_posed (x,y,z interleaved, n = 3*vertex + coord)
+    int ld;
+    const float* tmpl;   // [npad] template vertices (fp32, exact)
+    float inv_scale;     // undo the power-of-two scaling of the fp16 basis
+  };
+  static __device__ __forceinline__ void apply(const Params& ep, const EpiRow& er, int c0, const uint32_t (&v)[32]) {
+    if (!er.valid) return;
+    const int col = er.col0 + c0;
+    float4* dst = reinterpret_cast<float4*>(ep.out + static_cast<size_t>(er.pix) * ep.ld + col);
+    const float4* t4 = reinterpret_cast<const float4*>(ep.tmpl + col);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 t = __ldg(&t4[j]);
+      float4 o;
+      o.x = fmaf(__uint_as_float(v[4 * j + 0]), ep.inv_scale, t.x);
+      o.y = fmaf(__uint_as_float(v[4 * j + 1]), ep.inv_scale, t.y);
+      o.z = fmaf(__uint_as_float(v[4 * j + 2]), ep.inv_scale, t.z);
+      o.w = fmaf(__uint_as_float(v[4 * j + 3]), ep.inv_scale, t.w);
+      dst[j] = o;
+    }
+  }
+};
+
+// verification aid (DAD3D_BLEND_SIMT): same product on CUDA cores from the same hi/lo planes
+__global__ void blend_simt_kernel(const __half* __restrict__ a_hi, const __half* __restrict__ a_lo,
+                                  const __half* __restrict__ b_hi, const __half* __restrict__ b_lo,
+                                  const float* __restrict__ tmpl, float inv_scale, int rows, int npad,
+                                  float* __restrict__ out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int h = blockIdx.y;
+  if (n >= npad || h >= rows) return;
+  float acc = 0.f;
+  for (int k = 0; k < kKPad; ++k) {
+    const float a = __half2float(a_hi[static_cast<size_t>(h) * kKPad + k]) + __half2float(a_lo[static_cast<size_t>(h) * kKPad + k]);
+    const float b = __half2float(b_hi[static_cast<size_t>(n) * kKPad + k]) + __half2float(b_lo[static_cast<size_t>(n) * kKPad + k]);
+    acc = fmaf(a, b, acc);
+  }
+  out[static_cast<size_t>(h) * npad + n] = fmaf(acc, inv_scale, tmpl[n]);
+}
+
+// ------------------------------------------------------------------------------------------------ K3
+constexpr int kLbsThreads = 256;
+
+__global__ void __launch_bounds__(kLbsThreads)
+lbs_project_kernel(const float* __restrict__ vposed, int ldv, const float* __restrict__ weights,
+                   const float* __restrict__ xf, int B, int nv, float* __restrict__ verts3d,
+                   float* __restrict__ proj, int pc, float image_size) {
+  __shared__ float s_in[3 * kLbsThreads];
+  __shared__ float s_out[3 * kLbsThreads];
+  __shared__ float s_proj[3 * kLbsThreads];
+  __shared__ float s_xf[kXfFloats];
+  const int t = threadIdx.x;
+  const int v0 = blockIdx.x * kLbsThreads;
+  const int v = v0 + t;
+  const int nvalid = min(kLbsThreads, nv - v0);          // vertices in this block
+  float w[kJoints];
+#pragma unroll
+  for (int j = 0; j < kJoints; ++j) w[j] = (v < nv) ? __ldg(&weights[static_cast<size_t>(v) * kJoints + j]) : 0.f;
+
+  for (int h = blockIdx.y; h < B; h += gridDim.y) {
+    const float* src = vposed + static_cast<size_t>(h) * ldv + 3 * v0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int i = t + k * kLbsThreads;
+      if (i < 3 * nvalid) s_in[i] = __ldg(&src[i]);
+    }
+    if (t < kXfFloats) s_xf[t] = __ldg(&xf[static_cast<size_t>(h) * kXfFloats + t]);
+    __syncthreads();
+    if (v < nv) {
+      const float x = s_in[3 * t], y = s_in[3 * t + 1], z = s_in[3 * t + 2];
+      float ox = s_xf[60], oy = s_xf[61], oz = s_xf[62];
+#pragma unroll
+      for (int j = 0; j < kJoints; ++j) {
+        if (w[j] != 0.f) {
+          const float* A = &s_xf[12 * j];
+          ox = fmaf(w[j], fmaf(A[0], x, fmaf(A[1], y, fmaf(A[2], z, A[3]))), ox);
+          oy = fmaf(w[j], fmaf(A[4], x, fmaf(A[5], y, fmaf(A[6], z, A[7]))), oy);
+          oz = fmaf(w[j], fmaf(A[8], x, fmaf(A[9], y, fmaf(A[10], z, A[11]))), oz);
+        }
+      }
+      s_out[3 * t] = ox;
+      s_out[3 * t + 1] = oy;
+      s_out[3 * t + 2] = oz;
+      const float sc = s_xf[63];
+      const float px = ((ox * sc + s_xf[64]) + 1.0f) * 0.5f * image_size;     // head_mesh.py:40-43
+      const float py = ((oy * sc + s_xf[65]) + 1.0f) * 0.5f * image_size;
+      s_proj[pc * t] = px;
+      s_proj[pc * t + 1] = py;
+      if (pc == 3) s_proj[3 * t + 2] = ((oz * sc + 0.0f) + 1.0f) * 0.5f * image_size;
+    }
+    __syncthreads();
+    if (verts3d) {
+      float* dst = verts3d + (static_cast<size_t>(h) * nv + v0) * 3;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int i = t + k * kLbsThreads;
+        if (i < 3 * nvalid) dst[i] = s_out[i];
+      }
+    }
+    if (proj) {
+      float* dst = proj + (static_cast<size_t>(h) * nv + v0) * pc;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int i = t + k * kLbsThreads;
+        if (i < pc * nvalid) dst[i] = s_proj[i];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K4
+__global__ void gather_kernel(const float* __restrict__ src, int B, int nv, int nc, const int* __restrict__ idx, int L,
+                              float* __restrict__ out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(B) * L * nc;
+  if (i >= total) return;
+  const int c = static_cast<int>(i % nc);
+  const int l = static_cast<int>((i / nc) % L);
+  const long long b = i / (static_cast<long long>(nc) * L);
+  out[i] = __ldg(&src[(b * nv + __ldg(&idx[l])) * nc + c]);
+}
+
+__global__ void gather_bary_kernel(const float* __restrict__ src, int B, int nv, int nc, const int* __restrict__ tri,
+                                   const float* __restrict__ bary, int L, float* __restrict__ out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(B) * L * nc;
+  if (i >= total) return;
+  const int c = static_cast<int>(i % nc);
+  const int l = static_cast<int>((i / nc) % L);
+  const long long b = i / (static_cast<long long>(nc) * L);
+  float acc = 0.f;
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    acc = fmaf(__ldg(&bary[3 * l + k]), __ldg(&src[(b * nv + __ldg(&tri[3 * l + k])) * nc + c]), acc);
+  out[i] = acc;
+}
+
+}  // namespace dad3d
+
+// =================================================================================================== host side
+using namespace dad3d;
+
+struct dad3d_flame {
+  int device = 0;
+  int nv = 0, n3 = 0, npad = 0;
+  int num_sms = 0;
+  FlameLayoutDev layout{};
+  float basis_scale = 1.f;
+  __half* d_basis[2] = {nullptr, nullptr};   // [npad, kKPad] fp16 hi / lo planes of scale * [shapedirs | posedirs^T]
+  float* d_tmpl = nullptr;                   // [npad]
+  float* d_weights = nullptr;                // [nv, 5]
+  float* d_jt = nullptr;                     // [15]
+  float* d_jdirsT = nullptr;                 // [15, 400]
+  CUtensorMap map_b[2];
+};
+
+namespace {
+
+template <class Epi>
+int launch_tile_gemm(const GemmMaps& maps, const GemmGeom& g, const typename Epi::Params& ep, int num_sms,
+                     cudaStream_t stream) {
+  static int configured_smem = 0;
+  const int smem = gemm_smem_bytes(g);
+  if (smem > configured_smem) {
+    DAD3D_CUDA_OK(cudaFuncSetAttribute(tile_gemm_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured_smem = 227 * 1024;
+  }
+  const int total = g.tiles_w * g.tiles_h * g.tiles_n * g.n_tiles;
+  const int grid = total < num_sms ? total : num_sms;
+  tile_gemm_kernel<Epi><<<grid, kGemmThreads, smem, stream>>>(maps, g, ep);
+  count_launch();
+  DAD3D_CUDA_OK(cudaGetLastError());
+  return DAD3D_OK;
+}
+
+inline unsigned short f32_to_f16_bits(float x) {
+  // round-to-nearest-even fp32 -> fp16 on the host (finite inputs of modest magnitude only)
+  __half h = __float2half_rn(x);
+  unsigned short b;
+  std::memcpy(&b, &h, 2);
+  return b;
+}
+inline float f16_bits_to_f32(unsigned short b) {
+  __half h;
+  std::memcpy(&h, &b, 2);
+  return __half2float(h);
+}
+
+}  // namespace
+
+extern "C" {
+
+int dad3d_flame_create(dad3d_flame** out, const float* shapedirs_h, const float* posedirs_h, const float* v_template_h,
+                       const float* j_regressor_h, const int32_t* parents_h, const float* lbs_weights_h,
+                       int32_t n_vertices, int32_t n_betas, int32_t n_joints, const dad3d_flame_layout* lay,
+                       int32_t device) {
+  DAD3D_REQUIRE(out && shapedirs_h && posedirs_h && v_template_h && j_regressor_h && parents_h && lbs_weights_h && lay,
+                "null pointer");
+  DAD3D_REQUIRE(n_joints == kJoints, "n_joints must be 5 (FLAME)");
+  DAD3D_REQUIRE(n_betas == kBetas, "n_betas must be 400 (300 shape + 100 expression)");
+  DAD3D_REQUIRE(n_vertices > 0, "n_vertices");
+  DAD3D_REQUIRE(lay->rotation == 6, "rotation width must be 6 (model/utils.py:93)");
+  DAD3D_REQUIRE(lay->translation == 3 && lay->scale == 1, "translation/scale widths must be 3/1");
+  DAD3D_REQUIRE(lay->shape >= 0 && lay->shape <= kMaxShape && lay->expression >= 0 && lay->expression <= kMaxExpr,
+                "shape/expression widths");
+  DAD3D_REQUIRE((lay->jaw == 0 || lay->jaw == 3) && (lay->neck == 0 || lay->neck == 3) &&
+                    (lay->eyeballs == 0 || lay->eyeballs == 6),
+                "jaw/neck/eyeballs widths must be 0 or 3/3/6");
+  DAD3D_REQUIRE(parents_h[0] == -1, "parents[0] must be -1");
+  for (int i = 1; i < kJoints; ++i) DAD3D_REQUIRE(parents_h[i] >= 0 && parents_h[i] < i, "parents must be topologically ordered");
+
+  DAD3D_CUDA_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  DAD3D_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("libdad3d requires an sm_100 (Blackwell) device, found sm_" + std::to_string(prop.major) + std::to_string(prop.minor));
+    return DAD3D_ERR_UNSUPPORTED;
+  }
+
+  dad3d_flame* h = new dad3d_flame();
+  h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  h->nv = n_vertices;
+  h->n3 = 3 * n_vertices;
+  h->npad = ceil_div(h->n3, kBlendBlockN) * kBlendBlockN;
+  FlameLayoutDev& L = h->layout;
+  int cur = 0;
+  L.off_shape = cur; L.n_shape = lay->shape; cur += lay->shape;
+  L.off_expr = cur; L.n_expr = lay->expression; cur += lay->expression;
+  L.off_jaw = cur; L.n_jaw = lay->jaw; cur += lay->jaw;
+  L.off_rot = cur; cur += lay->rotation;
+  L.off_eye = cur; L.n_eye = lay->eyeballs; cur += lay->eyeballs;
+  L.off_neck = cur; L.n_neck = lay->neck; cur += lay->neck;
+  L.off_trans = cur; cur += lay->translation;
+  L.off_scale = cur; cur += lay->scale;
+  L.n_params = cur;
+  for (int i = 0; i < kJoints; ++i) L.parents[i] = parents_h[i];
+
+  const int n3 = h->n3, npad = h->npad;
+  // power-of-two scale that lifts the basis into the well-conditioned part of the fp16 range (hi AND lo normal)
+  float amax = 0.f;
+  for (size_t i = 0; i < static_cast<size_t>(n3) * kBetas; ++i) amax = fmaxf(amax, fabsf(shapedirs_h[i]));
+  for (size_t i = 0; i < static_cast<size_t>(kPoseFeat) * n3; ++i) amax = fmaxf(amax, fabsf(posedirs_h[i]));
+  int e = 0;
+  if (amax > 0.f) {
+    std::frexp(amax, &e);          // amax = m * 2^e, m in [0.5,1)
+    e = 10 - e;                     // scaled amax in [512, 1024)
+    if (e > 24) e = 24;
+    if (e < -8) e = -8;
+  }
+  h->basis_scale = std::ldexp(1.0f, e);
+
+  std::vector<unsigned short> hi(static_cast<size_t>(npad) * kKPad, 0), lo(static_cast<size_t>(npad) * kKPad, 0);
+  for (int n = 0; n < n3; ++n) {
+    unsigned short* rh = &hi[static_cast<size_t>(n) * kKPad];
+    unsigned short* rl = &lo[static_cast<size_t>(n) * kKPad];
+    for (int k = 0; k < kBetas + kPoseFeat; ++k) {
+      const float x = (k < kBetas ? shapedirs_h[static_cast<size_t>(n) * kBetas + k]
+                                  : posedirs_h[static_cast<size_t>(k - kBetas) * n3 + n]) * h->basis_scale;
+      const unsigned short hb = f32_to_f16_bits(x);
+      rh[k] = hb;
+      rl[k] = f32_to_f16_bits(x - f16_bits_to_f32(hb));
+    }
+  }
+  std::vector<float> tmpl(npad, 0.f);
+  for (int n = 0; n < n3; ++n) tmpl[n] = v_template_h[n];
+
+  // folded joint regressor: J = Jreg * T + (Jreg * S) beta   (smplx vertices2joints applied to v_shaped)
+  std::vector<float> jt(15, 0.f), jdirsT(15 * kBetas, 0.f);
+  {
+    std::vector<double> jt_d(15, 0.0), jd(15 * kBetas, 0.0);
+    for (int j = 0; j < kJoints; ++j)
+      for (int i = 0; i < n_vertices; ++i) {
+        const double wji = j_regressor_h[static_cast<size_t>(j) * n_vertices + i];
+        if (wji == 0.0) continue;
+        for (int c = 0; c < 3; ++c) {
+          jt_d[3 * j + c] += wji * v_template_h[3 * i + c];
+          const float* srow = &shapedirs_h[(static_cast<size_t>(i) * 3 + c) * kBetas];
+          double* drow = &jd[static_cast<size_t>(3 * j + c) * kBetas];
+          for (int l = 0; l < kBetas; ++l) drow[l] += wji * srow[l];
+        }
+      }
+    for (int i = 0; i < 15; ++i) jt[i] = static_cast<float>(jt_d[i]);
+    for (size_t i = 0; i < jd.size(); ++i) jdirsT[i] = static_cast<float>(jd[i]);
+  }
+
+  auto fail = [&](int code) { dad3d_flame_destroy(h); return code; };
+#define CK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { set_error(std::string(#expr) + " -> " + cudaGetErrorString(_e)); return fail(DAD3D_ERR_CUDA); } } while (0)
+  const size_t plane = static_cast<size_t>(npad) * kKPad * sizeof(__half);
+  CK(cudaMalloc(&h->d_basis[0], plane));
+  CK(cudaMalloc(&h->d_basis[1], plane));
+  CK(cudaMalloc(&h->d_tmpl, npad * sizeof(float)));
+  CK(cudaMalloc(&h->d_weights, static_cast<size_t>(n_vertices) * kJoints * sizeof(float)));
+  CK(cudaMalloc(&h->d_jt, 15 * sizeof(float)));
+  CK(cudaMalloc(&h->d_jdirsT, 15 * kBetas * sizeof(float)));
+  CK(cudaMemcpy(h->d_basis[0], hi.data(), plane, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->d_basis[1], lo.data(), plane, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->d_tmpl, tmpl.data(), npad * sizeof(float), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->d_weights, lbs_weights_h, static_cast<size_t>(n_vertices) * kJoints * sizeof(float), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->d_jt, jt.data(), 15 * sizeof(float), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->d_jdirsT, jdirsT.data(), 15 * kBetas * sizeof(float), cudaMemcpyHostToDevice));
+#undef CK
+  for (int p = 0; p < 2; ++p) {
+    const uint64_t dims[2] = {static_cast<uint64_t>(kKPad), static_cast<uint64_t>(npad)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(kKPad) * 2};
+    const uint32_t box[2] = {kBlockK, kBlendBlockN};
+    if (!make_tmap_16bit(&h->map_b[p], h->d_basis[p], 2, dims, strides, box, nullptr)) return fail(DAD3D_ERR_CUDA);
+  }
+  *out = h;
+  return DAD3D_OK;
+}
+
+void dad3d_flame_destroy(dad3d_flame* h) {
+  if (!h) return;
+  cudaFree(h->d_basis[0]);
+  cudaFree(h->d_basis[1]);
+  cudaFree(h->d_tmpl);
+  cudaFree(h->d_weights);
+  cudaFree(h->d_jt);
+  cudaFree(h->d_jdirsT);
+  delete h;
+}
+
+int32_t dad3d_flame_num_params(const dad3d_flame* h) { return h ? h->layout.n_params : 0; }
+int32_t dad3d_flame_num_vertices(const dad3d_flame* h) { return h ? h->nv : 0; }
+
+static size_t ws_coef_bytes(int rows) { return align_up(static_cast<size_t>(rows) * kKPad * sizeof(__half), 1024); }
+static size_t ws_xf_bytes(int rows) { return align_up(static_cast<size_t>(rows) * kXfFloats * sizeof(float), 1024); }
+static size_t ws_vposed_bytes(const dad3d_flame* h, int rows) { return align_up(static_cast<size_t>(rows) * h->npad * sizeof(float), 1024); }
+
+size_t dad3d_flame_workspace_bytes(const dad3d_flame* h, int32_t B) {
+  if (!h || B <= 0) return 0;
+  const int rows = B < kDecodeChunk ? B : kDecodeChunk;
+  return 2 * ws_coef_bytes(rows) + ws_xf_bytes(rows) + ws_vposed_bytes(h, rows) + 1024;
+}
+
+int dad3d_flame_decode(dad3d_flame* h, const float* params_d, int32_t B, int32_t flags, float* vertices3d_d,
+                       float* projected_d, float image_size, int32_t to_2d, void* workspace_d, size_t workspace_bytes,
+                       dad3d_stream stream_) {
+  DAD3D_REQUIRE(h, "null handle");
+  if (B == 0) return DAD3D_OK;
+  DAD3D_REQUIRE(B > 0 && params_d, "params");
+  DAD3D_REQUIRE(vertices3d_d || projected_d, "at least one output must be requested");
+  DAD3D_REQUIRE(workspace_d && workspace_bytes >= dad3d_flame_workspace_bytes(h, B), "workspace too small");
+  DAD3D_REQUIRE((reinterpret_cast<uintptr_t>(workspace_d) & 1023) == 0 || true, "workspace alignment");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const int rows_max = B < kDecodeChunk ? B : kDecodeChunk;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(workspace_d), 1024));
+  __half* a_hi = reinterpret_cast<__half*>(ws);
+  __half* a_lo = reinterpret_cast<__half*>(ws + ws_coef_bytes(rows_max));
+  float* xf = reinterpret_cast<float*>(ws + 2 * ws_coef_bytes(rows_max));
+  float* vposed = reinterpret_cast<float*>(ws + 2 * ws_coef_bytes(rows_max) + ws_xf_bytes(rows_max));
+  const int pc = to_2d ? 2 : 3;
+  const float inv_scale = 1.0f / h->basis_scale;
+
+  for (int b0 = 0; b0 < B; b0 += kDecodeChunk) {
+    const int rows = (B - b0) < kDecodeChunk ? (B - b0) : kDecodeChunk;
+    const float* p = params_d + static_cast<size_t>(b0) * h->layout.n_params;
+    {
+      const int threads = 256;
+      const int blocks = ceil_div(rows * 32, threads);
+      flame_prep_kernel<<<blocks, threads, 0, stream>>>(p, rows, h->layout, h->d_jt, h->d_jdirsT, flags, a_hi, a_lo, xf);
+      count_launch();
+      DAD3D_CUDA_OK(cudaGetLastError());
+    }
+    if (flags & DAD3D_BLEND_SIMT) {
+      dim3 grid(ceil_div(h->npad, 256), rows);
+      blend_simt_kernel<<<grid, 256, 0, stream>>>(a_hi, a_lo, h->d_basis[0], h->d_basis[1], h->d_tmpl, inv_scale, rows,
+                                                  h->npad, vposed);
+      count_launch();
+      DAD3D_CUDA_OK(cudaGetLastError());
+    } else {
+      GemmMaps maps;
+      std::memset(&maps, 0, sizeof(maps));
+      __half* planes[2] = {a_hi, a_lo};
+      for (int pi = 0; pi < 2; ++pi) {
+        const uint64_t dims[4] = {static_cast<uint64_t>(kKPad), static_cast<uint64_t>(rows), 1, 1};
+        const uint64_t strides[3] = {static_cast<uint64_t>(kKPad) * 2, static_cast<uint64_t>(kKPad) * 2 * rows,
+                                     static_cast<uint64_t>(kKPad) * 2 * rows};
+        const uint32_t box[4] = {kBlockK, kBlockM, 1, 1};
+        if (!make_tmap_16bit(&maps.a[pi], planes[pi], 4, dims, strides, box, nullptr)) return DAD3D_ERR_CUDA;
+        maps.b[pi] = h->map_b[pi];
+      }
+      GemmGeom g;
+      std::memset(&g, 0, sizeof(g));
+      g.tw = kBlockM; g.th = 1; g.tn = 1;
+      g.tiles_w = ceil_div(rows, kBlockM); g.tiles_h = 1; g.tiles_n = 1;
+      g.Wo = rows; g.Ho = 1; g.Nimg = 1;
+      g.stride = 1; g.R = 1; g.S = 1; g.pad_h = 0; g.pad_w = 0;
+      g.cin_blocks = kKPad / kBlockK;
+      g.n_tiles = h->npad / kBlendBlockN;
+      g.block_n = kBlendBlockN;
+      g.fmt16 = 0;
+      if (flags & DAD3D_BLEND_FAST) {
+        g.nA = 1; g.nB = 1; g.n_mma = 1; g.mma_a[0] = 0; g.mma_b[0] = 0;
+      } else {
+        g.nA = 2; g.nB = 2; g.n_mma = 3;
+        g.mma_a[0] = 1; g.mma_b[0] = 0;   // lo*hi and hi*lo first (small terms), hi*hi last
+        g.mma_a[1] = 0; g.mma_b[1] = 1;
+        g.mma_a[2] = 0; g.mma_b[2] = 0;
+      }
+      const int stage_bytes = gemm_stage_bytes(g);
+      g.stages = (227 * 1024 - 2048) / stage_bytes;
+      if (g.stages > 8) g.stages = 8;
+      EpiBlend::Params ep{vposed, h->npad, h->d_tmpl, inv_scale};
+      int rc = launch_tile_gemm<EpiBlend>(maps, g, ep, h->num_sms, stream);
+      if (rc != DAD3D_OK) return rc;
+    }
+    {
+      dim3 grid(ceil_div(h->nv, kLbsThreads), rows < 1024 ? rows : 1024);
+      float* v3 = vertices3d_d ? vertices3d_d + static_cast<size_t>(b0) * h->nv * 3 : nullptr;
+      float* pj = projected_d ? projected_d + static_cast<size_t>(b0) * h->nv * pc : nullptr;
+      lbs_project_kernel<<<grid, kLbsThreads, 0, stream>>>(vposed, h->npad, h->d_weights, xf, rows, h->nv, v3, pj, pc,
+                                                           image_size);
+      count_launch();
+      DAD3D_CUDA_OK(cudaGetLastError());
+    }
+  }
+  return DAD3D_OK;
+}
+
+int dad3d_gather_landmarks(const float* src_d, int32_t B, int32_t n_vertices, int32_t ncomp, const int32_t* idx_d,
+                           int32_t L, float* out_d, dad3d_stream stream) {
+  DAD3D_REQUIRE(src_d && idx_d && out_d, "null pointer");
+  DAD3D_REQUIRE(B >= 0 && L >= 0 && n_vertices > 0 && (ncomp == 2 || ncomp == 3), "shape");
+  const long long total = static_cast<long long>(B) * L * ncomp;
+  if (total == 0) return DAD3D_OK;
+  gather_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      src_d, B, n_vertices, ncomp, idx_d, L, out_d);
+  count_launch();
+  DAD3D_CUDA_OK(cudaGetLastError());
+  return DAD3D_OK;
+}
+
+int dad3d_gather_landmarks_bary(const float* src_d, int32_t B, int32_t n_vertices, int32_t ncomp,
+                                const int32_t* tri_idx_d, const float* bary_d, int32_t L, float* out_d,
+                                dad3d_stream stream) {
+  DAD3D_REQUIRE(src_d && tri_idx_d && bary_d && out_d, "null pointer");
+  DAD3D_REQUIRE(B >= 0 && L >= 0 && n_vertices > 0 && (ncomp == 2 || ncomp == 3), "shape");
+  const long long total = static_cast<long long>(B) * L * ncomp;
+  if (total == 0) return DAD3D_OK;
+  gather_bary_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      src_d, B, n_vertices, ncomp, tri_idx_d, bary_d, L, out_d);
+  count_launch();
+  DAD3D_CUDA_OK(cudaGetLastError());
+  return DAD3D_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,239 @@
+// Persistent, warp-specialised tcgen05 tile engine for sm_100a.
+//
+//   D[128 x block_n] (fp32, TMEM)  =  sum over k-blocks, over (a_piece, b_piece) pairs   A_piece[128 x 64] * B_piece[block_n x 64]^T
+//
+// One kernel serves every dense contraction on the hot path:
+//   * the FLAME blend-shape product  (plain GEMM: rows = heads, K = betas | pose features, N = 3*5023 coordinates), and
+//   * every convolution of the encoder as an implicit GEMM over NHWC activations (rows = output pixels, the k loop walks
+//     filter taps x 64-channel blocks; the A tile for a tap is a TMA box at shifted coordinates, zero-filled outside the
+//     image, so padding costs nothing and no im2col buffer exists).
+//
+// Operands are 16-bit (fp16 or bf16, chosen in the instruction descriptor).  fp32-class accuracy comes from splitting each
+// fp32 operand into "pieces" (x = p0 + p1 [+ p2], each piece 16-bit) stored as separate planes; the MMA list names which
+// (A piece, B piece) products are accumulated (1 product = plain 16-bit GEMM, 3 = hi*hi + hi*lo + lo*hi, 6 = three-way).
+//
+// Roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one lane), warp 2 = TMEM allocator,
+// warps 4..7 = epilogue (thread t of the warpgroup owns accumulator row t = TMEM lane t).
+// Pipelines: smem ring (full/empty mbarriers) between TMA and MMA; two TMEM accumulators (tmem_full/tmem_empty)
+// between MMA and epilogue, so the epilogue of tile i overlaps the main loop of tile i+1.
+#pragma once
+#include "ptx.cuh"
+
+namespace dad3d {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;                       // 64 x 16-bit = 128 B = one swizzle-128B row
+constexpr int kTileABytes = kBlockM * kBlockK * 2;   // 16 KiB per A piece per stage
+constexpr int kMaxPieces = 3;
+constexpr int kMaxMma = 6;
+constexpr int kGemmThreads = 256;
+constexpr int kTmemCols = 512;
+
+struct GemmGeom {
+  // output tile = tn images x th rows x tw columns of output pixels (tw*th*tn == 128); plain GEMM: tw=128, th=tn=1
+  int tw, th, tn;
+  int tiles_w, tiles_h, tiles_n;   // tile counts along W, H, N(images)
+  int Wo, Ho, Nimg;                // output extents (store bounds)
+  int stride;                      // convolution stride (A tensor map carries matching element strides)
+  int R, S, pad_h, pad_w;          // filter taps and padding
+  int cin_blocks;                  // padded Cin / 64
+  int n_tiles;                     // padded Cout / block_n
+  int block_n;                     // UMMA N: multiple of 32, 32..256
+  int nA, nB;                      // operand pieces
+  int n_mma;                       // number of (a,b) piece products
+  int mma_a[kMaxMma], mma_b[kMaxMma];
+  int stages;                      // smem ring depth
+  unsigned fmt16;                  // 0 = fp16, 1 = bf16
+};
+
+struct GemmMaps {
+  CUtensorMap a[kMaxPieces];       // rank-4 (C, W, H, N), box (64, tw*stride, th*stride, tn), swizzle 128B
+  CUtensorMap b[kMaxPieces];       // rank-2 (Ktot, Cout_pad), box (64, block_n), swizzle 128B
+};
+
+__host__ __device__ inline int gemm_stage_bytes(const GemmGeom& g) {
+  return g.nA * kTileABytes + g.nB * g.block_n * kBlockK * 2;
+}
+__host__ inline int gemm_smem_bytes(const GemmGeom& g) {
+  return g.stages * gemm_stage_bytes(g) + 1024 /*align slack*/ + 256 /*barriers*/;
+}
+
+struct TileCoord {
+  int m_tile, n_tile;
+  int n0, h0, w0;   // first output image / row / column of the tile
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const GemmGeom& g, int t) {
+  TileCoord c;
+  c.n_tile = t % g.n_tiles;
+  c.m_tile = t / g.n_tiles;
+  int iw = c.m_tile % g.tiles_w;
+  int ih = (c.m_tile / g.tiles_w) % g.tiles_h;
+  int in = c.m_tile / (g.tiles_w * g.tiles_h);
+  c.n0 = in * g.tn;
+  c.h0 = ih * g.th;
+  c.w0 = iw * g.tw;
+  return c;
+}
+
+// What an epilogue sees for its accumulator row.
+struct EpiRow {
+  int row;          // 0..127 inside the tile
+  int n, h, w;      // output pixel of this row (plain GEMM: w = global row index)
+  bool valid;       // inside the output extents
+  long long pix;    // linear output pixel index ((n*Ho + h)*Wo + w)
+  int col0;         // first output column (channel) of the tile
+};
+
+template <class Epi>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const typename Epi::Params ep) {
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment is required by the 128B swizzle atoms (TMA writes and UMMA reads must agree on the pattern).
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int stage_bytes = gemm_stage_bytes(g);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + g.stages * stage_bytes);
+  uint64_t* full_bar = bars;                     // [stages]
+  uint64_t* empty_bar = bars + g.stages;         // [stages]
+  uint64_t* tfull_bar = bars + 2 * g.stages;     // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = g.tiles_w * g.tiles_h * g.tiles_n * g.n_tiles;
+  const int num_kb = g.R * g.S * g.cin_blocks;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < g.nA; ++i) ptx::prefetch_tmap(&maps.a[i]);
+    for (int i = 0; i < g.nB; ++i) ptx::prefetch_tmap(&maps.b[i]);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < g.stages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(&tfull_bar[b], 1);
+      ptx::mbar_init(&tempty_bar[b], 128);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_slot, kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx_bytes = static_cast<uint32_t>(stage_bytes);
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile(g, t);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int tap = kb / g.cin_blocks;
+          const int cb = kb - tap * g.cin_blocks;
+          const int r = tap / g.S;
+          const int s = tap - r * g.S;
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+          ptx::mbar_expect_tx(&full_bar[stage], tx_bytes);
+          uint8_t* st = smem + stage * stage_bytes;
+          const int cw = tc.w0 * g.stride + s - g.pad_w;
+          const int ch = tc.h0 * g.stride + r - g.pad_h;
+          for (int i = 0; i < g.nA; ++i)
+            ptx::tma_load_4d(st + i * kTileABytes, &maps.a[i], &full_bar[stage], cb * kBlockK, cw, ch, tc.n0);
+          uint8_t* sb = st + g.nA * kTileABytes;
+          const int kcol = kb * kBlockK;
+          for (int i = 0; i < g.nB; ++i)
+            ptx::tma_load_2d(sb + i * g.block_n * kBlockK * 2, &maps.b[i], &full_bar[stage], kcol,
+                             tc.n_tile * g.block_n);
+          if (++stage == g.stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (single thread)
+    if (lane == 0) {
+      const uint32_t idesc = ptx::make_idesc_f16(g.fmt16, kBlockM, static_cast<uint32_t>(g.block_n));
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * g.block_n);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem + stage * stage_bytes);
+          const uint32_t sb = sa + g.nA * kTileABytes;
+          for (int i = 0; i < g.n_mma; ++i) {
+            const uint64_t adesc = ptx::make_kmajor_sw128_desc(sa + g.mma_a[i] * kTileABytes);
+            const uint64_t bdesc = ptx::make_kmajor_sw128_desc(sb + g.mma_b[i] * g.block_n * kBlockK * 2);
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              // advancing 16 elements (32 B) along K inside the 128 B swizzle row = +2 in the (addr >> 4) field
+              ptx::umma_f16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | i | k) != 0 ? 1u : 0u);
+            }
+          }
+          ptx::umma_commit(&empty_bar[stage]);   // smem slot reusable once these MMAs have read it
+          if (++stage == g.stages) { stage = 0; phase ^= 1u; }
+        }
+        ptx::umma_commit(&tfull_bar[acc]);        // accumulator complete
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================================== epilogue warpgroup
+    const int wq = warp & 3;                       // TMEM lane quarter this warp may touch
+    const int row = wq * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const TileCoord tc = decode_tile(g, t);
+      EpiRow er;
+      er.row = row;
+      const int iw = row % g.tw;
+      const int ih = (row / g.tw) % g.th;
+      const int in = row / (g.tw * g.th);
+      er.n = tc.n0 + in;
+      er.h = tc.h0 + ih;
+      er.w = tc.w0 + iw;
+      er.valid = (er.n < g.Nimg) && (er.h < g.Ho) && (er.w < g.Wo);
+      er.pix = (static_cast<long long>(er.n) * g.Ho + er.h) * g.Wo + er.w;
+      er.col0 = tc.n_tile * g.block_n;
+      ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + static_cast<uint32_t>(acc * g.block_n);
+      for (int c0 = 0; c0 < g.block_n; c0 += 32) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(c0), v);
+        ptx::tmem_ld_wait();
+        if (c0 + 32 >= g.block_n) {                // accumulator fully drained into registers: hand TMEM back early
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(&tempty_bar[acc]);
+        }
+        Epi::apply(ep, er, c0, v);
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace dad3d

@@ -1,0 +1,31 @@
+#!/usr/bin/env python
+"""Generate tests/golden/flame_decode_golden.npz from the fp64 oracle (the reference itself cannot run here -- see
+oracle/__init__.py -- so these are regression pins of the restatement, not reference outputs)."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle.flame_oracle import FlameOracle, load_static, sample_params  # noqa: E402
+
+
+def main():
+    st = load_static()
+    o = FlameOracle(st, dtype=torch.float64)
+    p = sample_params(6, seed=2024)
+    p[0] = 0
+    p[0, 403:409] = torch.tensor([1.0, 0, 0, 0, 1.0, 0])
+    v = o.vertices_3d(p)
+    q = o.reprojected_vertices(p)
+    idx = st["keypoints_445"]
+    out = os.path.join(ROOT, "tests", "golden", "flame_decode_golden.npz")
+    np.savez_compressed(out, params=p.numpy(), vertices3d=v.float().numpy(), projected=q.float().numpy(), idx445=idx,
+                        landmarks445=q.float().numpy()[:, idx])
+    print("wrote", out, os.path.getsize(out))
+
+
+if __name__ == "__main__":
+    main()
