@@ -1,0 +1,349 @@
+// Device code of the DAD-3DNet encoder (everything that is not the tcgen05 tile engine itself):
+//   EpiConv            fused conv epilogue: folded-BN bias, residual add / gate multiply, ReLU, split into bf16 pieces
+//   stem_conv_kernel   7x7/2 conv (Cin = 3) + folded BN + ReLU, fp32 CUDA cores, NCHW fp32 image -> NHWC fp32
+//   stem_pool_kernel   3x3/2 max-pool + split into pieces
+//   bifpn_fuse_kernel  fast-normalised weighted sum of 2-3 maps with nearest resampling (BiFPN node input)
+//   fusion_concat_kernel  [x | sigmoid(bilinear_align_corners(heatmap)) | p5] channel concat (FusionLayer input)
+//   gap_kernel         global average pool
+//   head_finalize_kernel  tanh*3 / identity / relu on the MLP outputs -> 3DMM params + 2D landmarks
+// Activations are NHWC with channels padded to a multiple of 64 and stored as P "piece" planes of bf16
+// (x = p0 + p1 + p2, see tile_gemm.cuh); plane p starts at base + p * plane_elems.
+#pragma once
+#include <cuda_bf16.h>
+
+#include "tile_gemm.cuh"
+
+namespace dad3d {
+
+// ------------------------------------------------------------------------------------------------ piece helpers
+__device__ __forceinline__ uint16_t bf16_bits(float x) { return __bfloat16_as_ushort(__float2bfloat16_rn(x)); }
+__device__ __forceinline__ float bf16_to_f32(uint16_t b) { return __uint_as_float(static_cast<uint32_t>(b) << 16); }
+
+// split x into NP bf16 pieces (round-to-nearest each, remainder carried exactly in fp32)
+template <int NP>
+__device__ __forceinline__ void split_bf16(float x, uint16_t (&p)[NP]) {
+  float r = x;
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    p[i] = bf16_bits(r);
+    r -= bf16_to_f32(p[i]);
+  }
+}
+
+struct ActView {            // read-only view of a piece tensor
+  const uint16_t* base;
+  long long plane;          // elements per plane
+  int planes;
+  int C;                    // channel stride (padded channel count)
+};
+__device__ __forceinline__ float act_load(const ActView& a, long long off) {
+  float s = 0.f;
+  for (int p = a.planes - 1; p >= 0; --p) s += bf16_to_f32(__ldg(a.base + p * a.plane + off));   // small pieces first
+  return s;
+}
+// 8 consecutive channels (16 B per plane)
+__device__ __forceinline__ void act_load8(const ActView& a, long long off, float (&v)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = 0.f;
+  for (int p = a.planes - 1; p >= 0; --p) {
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(a.base + p * a.plane + off));
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[2 * j] += __uint_as_float(w[j] << 16);
+      v[2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+    }
+  }
+}
+__device__ __forceinline__ void act_store8(uint16_t* base, long long plane, int planes, long long off, const float (&v)[8]) {
+  float r[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) r[j] = v[j];
+  for (int p = 0; p < planes; ++p) {
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint16_t lo = bf16_bits(r[2 * j]), hi = bf16_bits(r[2 * j + 1]);
+      r[2 * j] -= bf16_to_f32(lo);
+      r[2 * j + 1] -= bf16_to_f32(hi);
+      w[j] = static_cast<uint32_t>(lo) | (static_cast<uint32_t>(hi) << 16);
+    }
+    *reinterpret_cast<uint4*>(base + p * plane + off) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ conv epilogue
+struct EpiConv {
+  struct Params {
+    const float* bias;        // [Cout_pad] folded BN shift / conv bias
+    int relu;
+    int res_mode;             // 0 none, 1 add before ReLU (ResUnit), 2 multiply after bias (FusionLayer gate)
+    ActView res;              // same pixel indexing as the output
+    uint16_t* out;            // piece planes [planes][pix][ld_out]; may be null when only out_f32 is wanted
+    long long out_plane;
+    int out_planes;
+    int ld_out;
+    float* out_f32;           // optional fp32 copy [pix][ld_f32]
+    int ld_f32;
+  };
+  static __device__ __forceinline__ void apply(const Params& ep, const EpiRow& er, int c0, const uint32_t (&v)[32]) {
+    if (!er.valid) return;
+    const int col = er.col0 + c0;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {            // 4 groups of 8 channels
+      float x[8];
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + col + 8 * g));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + col + 8 * g + 4));
+      x[0] = __uint_as_float(v[8 * g + 0]) + b0.x;
+      x[1] = __uint_as_float(v[8 * g + 1]) + b0.y;
+      x[2] = __uint_as_float(v[8 * g + 2]) + b0.z;
+      x[3] = __uint_as_float(v[8 * g + 3]) + b0.w;
+      x[4] = __uint_as_float(v[8 * g + 4]) + b1.x;
+      x[5] = __uint_as_float(v[8 * g + 5]) + b1.y;
+      x[6] = __uint_as_float(v[8 * g + 6]) + b1.z;
+      x[7] = __uint_as_float(v[8 * g + 7]) + b1.w;
+      if (ep.res_mode != 0) {
+        float r[8];
+        act_load8(ep.res, er.pix * ep.res.C + col + 8 * g, r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = (ep.res_mode == 1) ? (x[j] + r[j]) : (x[j] * r[j]);
+      }
+      if (ep.relu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = fmaxf(x[j], 0.f);
+      }
+      if (ep.out) act_store8(ep.out, ep.out_plane, ep.out_planes, er.pix * ep.ld_out + col + 8 * g, x);
+      if (ep.out_f32) {
+        float4* d = reinterpret_cast<float4*>(ep.out_f32 + er.pix * ep.ld_f32 + col + 8 * g);
+        d[0] = make_float4(x[0], x[1], x[2], x[3]);
+        d[1] = make_float4(x[4], x[5], x[6], x[7]);
+      }
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ stem
+// 7x7 stride-2 pad-3 conv, 3 -> 64 channels, BN folded, ReLU.  in: NCHW fp32 [B,3,H,W]; out: NHWC fp32 [B,H/2,W/2,64].
+// Block = 16x16 output pixels; thread = one pixel, 64 accumulators; weights [147][64] and the 37x37x3 patch in smem.
+constexpr int kStemTile = 16;
+constexpr int kStemPatch = kStemTile * 2 + 5;    // 37
+__global__ void __launch_bounds__(256)
+stem_conv_kernel(const float* __restrict__ img, const float* __restrict__ w /*[147][64]*/, const float* __restrict__ bias,
+                 int H, int W, float* __restrict__ out) {
+  __shared__ float s_w[147 * 64];
+  __shared__ float s_in[3][kStemPatch][kStemPatch + 1];
+  const int Ho = H / 2, Wo = W / 2;
+  const int b = blockIdx.z;
+  const int oy0 = blockIdx.y * kStemTile, ox0 = blockIdx.x * kStemTile;
+  const int t = threadIdx.x;
+  for (int i = t; i < 147 * 64; i += 256) s_w[i] = __ldg(&w[i]);
+  const int iy0 = oy0 * 2 - 3, ix0 = ox0 * 2 - 3;
+  for (int i = t; i < 3 * kStemPatch * kStemPatch; i += 256) {
+    const int c = i / (kStemPatch * kStemPatch);
+    const int rem = i - c * kStemPatch * kStemPatch;
+    const int py = rem / kStemPatch, px = rem - py * kStemPatch;
+    const int iy = iy0 + py, ix = ix0 + px;
+    float val = 0.f;
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) val = __ldg(&img[((static_cast<size_t>(b) * 3 + c) * H + iy) * W + ix]);
+    s_in[c][py][px] = val;
+  }
+  __syncthreads();
+  const int ty = t / kStemTile, tx = t % kStemTile;
+  float acc[64];
+#pragma unroll
+  for (int o = 0; o < 64; ++o) acc[o] = 0.f;
+  for (int c = 0; c < 3; ++c)
+    for (int ky = 0; ky < 7; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 7; ++kx) {
+        const float xv = s_in[c][ty * 2 + ky][tx * 2 + kx];
+        const float4* wr = reinterpret_cast<const float4*>(&s_w[((c * 7 + ky) * 7 + kx) * 64]);
+#pragma unroll
+        for (int o = 0; o < 16; ++o) {
+          const float4 q = wr[o];
+          acc[4 * o + 0] = fmaf(xv, q.x, acc[4 * o + 0]);
+          acc[4 * o + 1] = fmaf(xv, q.y, acc[4 * o + 1]);
+          acc[4 * o + 2] = fmaf(xv, q.z, acc[4 * o + 2]);
+          acc[4 * o + 3] = fmaf(xv, q.w, acc[4 * o + 3]);
+        }
+      }
+  const int oy = oy0 + ty, ox = ox0 + tx;
+  if (oy < Ho && ox < Wo) {
+    float4* d = reinterpret_cast<float4*>(out + ((static_cast<size_t>(b) * Ho + oy) * Wo + ox) * 64);
+#pragma unroll
+    for (int o = 0; o < 16; ++o) {
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(bias) + o);
+      d[o] = make_float4(fmaxf(acc[4 * o] + bb.x, 0.f), fmaxf(acc[4 * o + 1] + bb.y, 0.f),
+                         fmaxf(acc[4 * o + 2] + bb.z, 0.f), fmaxf(acc[4 * o + 3] + bb.w, 0.f));
+    }
+  }
+}
+
+// MaxPool2d(3, stride 2, pad 1) over NHWC fp32 [B,Hi,Wi,64] -> pieces [B,Hi/2,Wi/2,64].  thread = 8 channels of a pixel.
+__global__ void stem_pool_kernel(const float* __restrict__ in, int B, int Hi, int Wi, uint16_t* __restrict__ out,
+                                 long long out_plane, int planes) {
+  const int Ho = Hi / 2, Wo = Wi / 2;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(B) * Ho * Wo * 8;
+  if (i >= total) return;
+  const int cg = static_cast<int>(i & 7);
+  const long long pix = i >> 3;
+  const int ox = static_cast<int>(pix % Wo);
+  const int oy = static_cast<int>((pix / Wo) % Ho);
+  const long long b = pix / (static_cast<long long>(Wo) * Ho);
+  float m[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+  for (int dy = -1; dy <= 1; ++dy) {
+    const int iy = oy * 2 + dy;
+    if (iy < 0 || iy >= Hi) continue;
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int ix = ox * 2 + dx;
+      if (ix < 0 || ix >= Wi) continue;
+      const float4* s = reinterpret_cast<const float4*>(in + ((b * Hi + iy) * Wi + ix) * 64 + cg * 8);
+      const float4 a = __ldg(s), c = __ldg(s + 1);
+      m[0] = fmaxf(m[0], a.x); m[1] = fmaxf(m[1], a.y); m[2] = fmaxf(m[2], a.z); m[3] = fmaxf(m[3], a.w);
+      m[4] = fmaxf(m[4], c.x); m[5] = fmaxf(m[5], c.y); m[6] = fmaxf(m[6], c.z); m[7] = fmaxf(m[7], c.w);
+    }
+  }
+  act_store8(out, out_plane, planes, pix * 64 + cg * 8, m);
+}
+
+// ------------------------------------------------------------------------------------------------ BiFPN node input
+// out[b,y,x,c] = w0*a[b,y,x,c] + w1*b1[nearest] (+ w2*b2[nearest]);  bifpn.py:111-129.  F.interpolate(mode="nearest"):
+// src = floor(dst * in / out)  (x2 up-sampling: dst>>1, /2 down-sampling: 2*dst).  thread = 8 channels of a pixel.
+struct FuseSrc {
+  ActView v;
+  int H, W;       // source extents
+  float w;
+};
+__global__ void bifpn_fuse_kernel(FuseSrc s0, FuseSrc s1, FuseSrc s2, int nsrc, int B, int H, int W, int C,
+                                  uint16_t* __restrict__ out, long long out_plane, int planes) {
+  const int cgs = C / 8;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(B) * H * W * cgs;
+  if (i >= total) return;
+  const int cg = static_cast<int>(i % cgs);
+  const long long pix = i / cgs;
+  const int x = static_cast<int>(pix % W);
+  const int y = static_cast<int>((pix / W) % H);
+  const long long b = pix / (static_cast<long long>(W) * H);
+  float acc[8], t[8];
+  act_load8(s0.v, pix * C + cg * 8, t);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = s0.w * t[j];
+  {
+    const int sy = (y * s1.H) / H, sx = (x * s1.W) / W;
+    act_load8(s1.v, ((b * s1.H + sy) * s1.W + sx) * C + cg * 8, t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += s1.w * t[j];
+  }
+  if (nsrc == 3) {
+    const int sy = (y * s2.H) / H, sx = (x * s2.W) / W;
+    act_load8(s2.v, ((b * s2.H + sy) * s2.W + sx) * C + cg * 8, t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += s2.w * t[j];
+  }
+  act_store8(out, out_plane, planes, pix * C + cg * 8, acc);
+}
+
+// ------------------------------------------------------------------------------------------------ FusionLayer input
+// out[b,y,x,:] = [ x[b,y,x,0:Cx] | sigmoid(bilinear_align_corners(heat))[0:Ch_pad] | p5[b,y,x,0:Cp] ]
+// (flame_regression.py:33-41).  heat is fp32 NHWC [B,Hh,Wh,ldh]; channels >= n_heat of the middle block are zero.
+__global__ void fusion_concat_kernel(ActView x, int Cx, const float* __restrict__ heat, int Hh, int Wh, int ldh,
+                                     int n_heat, int Ch_pad, ActView p5, int Cp, int B, int H, int W,
+                                     uint16_t* __restrict__ out, long long out_plane, int planes) {
+  const int Ct = Cx + Ch_pad + Cp;
+  const int cgs = Ct / 8;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(B) * H * W * cgs;
+  if (i >= total) return;
+  const int cg = static_cast<int>(i % cgs);
+  const long long pix = i / cgs;
+  const int c = cg * 8;
+  float v[8];
+  if (c < Cx) {
+    act_load8(x, pix * Cx + c, v);
+  } else if (c < Cx + Ch_pad) {
+    const int px = static_cast<int>(pix % W);
+    const int py = static_cast<int>((pix / W) % H);
+    const long long b = pix / (static_cast<long long>(W) * H);
+    // align_corners=True: src = dst * (in - 1) / (out - 1)
+    const float fy = (H > 1) ? py * (static_cast<float>(Hh - 1) / static_cast<float>(H - 1)) : 0.f;
+    const float fx = (W > 1) ? px * (static_cast<float>(Wh - 1) / static_cast<float>(W - 1)) : 0.f;
+    const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+    const int y1 = min(y0 + 1, Hh - 1), x1 = min(x0 + 1, Wh - 1);
+    const float ly = fy - y0, lx = fx - x0;
+    const int ch0 = c - Cx;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int ch = ch0 + j;
+      float r = 0.f;
+      if (ch < n_heat) {
+        const float v00 = __ldg(&heat[((b * Hh + y0) * Wh + x0) * ldh + ch]);
+        const float v01 = __ldg(&heat[((b * Hh + y0) * Wh + x1) * ldh + ch]);
+        const float v10 = __ldg(&heat[((b * Hh + y1) * Wh + x0) * ldh + ch]);
+        const float v11 = __ldg(&heat[((b * Hh + y1) * Wh + x1) * ldh + ch]);
+        const float top = v00 + (v01 - v00) * lx;          // same lerp form ATen's upsample_bilinear2d uses:
+        const float bot = v10 + (v11 - v10) * lx;          //   (1-l)*a + l*b evaluated as below
+        const float val = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+        (void)top; (void)bot;
+        r = 1.f / (1.f + expf(-val));
+      }
+      v[j] = r;
+    }
+  } else {
+    act_load8(p5, pix * Cp + (c - Cx - Ch_pad), v);
+  }
+  act_store8(out, out_plane, planes, pix * Ct + c, v);
+}
+
+// ------------------------------------------------------------------------------------------------ GAP
+// adaptive_avg_pool2d(., 1): [B,HW,C] -> [B,C] pieces.  thread = 8 channels of an image.
+__global__ void gap_kernel(ActView x, int B, int HW, int C, uint16_t* __restrict__ out, long long out_plane, int planes) {
+  const int cgs = C / 8;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * cgs) return;
+  const int cg = i % cgs;
+  const int b = i / cgs;
+  float acc[8], t[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int p = 0; p < HW; ++p) {
+    act_load8(x, (static_cast<long long>(b) * HW + p) * C + cg * 8, t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += t[j];
+  }
+  const float inv = 1.f / static_cast<float>(HW);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] *= inv;
+  act_store8(out, out_plane, planes, static_cast<long long>(b) * C + cg * 8, acc);
+}
+
+// ------------------------------------------------------------------------------------------------ heads
+// mlp_out [B, ld] fp32 = [shape 403 | pose 10 | landmarks 136 | pad]  ->  params [B,413] = [tanh(shape)*limit | pose],
+// landmarks [B,68,2] = relu(.)   (flame_regression.py:96-106)
+__global__ void head_finalize_kernel(const float* __restrict__ mlp_out, int ld, int B, float limit,
+                                     float* __restrict__ params, float* __restrict__ landmarks) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * 549) return;
+  const int b = i / 549, j = i - b * 549;
+  const float v = mlp_out[static_cast<size_t>(b) * ld + j];
+  if (j < 403) params[static_cast<size_t>(b) * 413 + j] = tanhf(v) * limit;
+  else if (j < 413) params[static_cast<size_t>(b) * 413 + j] = v;
+  else landmarks[static_cast<size_t>(b) * 136 + (j - 413)] = fmaxf(v, 0.f);
+}
+
+// heat-map NHWC fp32 [B,HW,ld] -> NCHW fp32 [B,68,HW] (the reference's OUTPUT_LANDMARKS_HEATMAP layout)
+__global__ void heatmap_export_kernel(const float* __restrict__ in, int ld, int B, int HW, int C,
+                                      float* __restrict__ out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(B) * C * HW;
+  if (i >= total) return;
+  const int p = static_cast<int>(i % HW);
+  const int c = static_cast<int>((i / HW) % C);
+  const long long b = i / (static_cast<long long>(HW) * C);
+  out[i] = __ldg(&in[(b * HW + p) * ld + c]);
+}
+
+}  // namespace dad3d

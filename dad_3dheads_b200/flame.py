@@ -171,6 +171,8 @@ class FlameDecoder:
         idx = idx.to(device=src.device, dtype=torch.int32).contiguous()
         B, V, nc = src.shape
         out = torch.empty(B, idx.numel(), nc, dtype=torch.float32, device=src.device)
+        if out.numel() == 0:
+            return out
         with torch.cuda.device(src.device):
             _lib.check(self.lib.dad3d_gather_landmarks(src.data_ptr(), B, V, nc, idx.data_ptr(), idx.numel(),
                                                        out.data_ptr(),
@@ -187,6 +189,8 @@ class FlameDecoder:
         B, V, nc = src.shape
         L = tri_idx.shape[0]
         out = torch.empty(B, L, nc, dtype=torch.float32, device=src.device)
+        if out.numel() == 0:
+            return out
         with torch.cuda.device(src.device):
             _lib.check(self.lib.dad3d_gather_landmarks_bary(src.data_ptr(), B, V, nc, tri_idx.data_ptr(),
                                                             bary.data_ptr(), L, out.data_ptr(),
