@@ -42,6 +42,15 @@ SIGNATURES = {
                                           C.c_void_p, C.c_void_p]),
     "dad3d_gather_landmarks_bary": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                                C.c_int32, C.c_void_p, C.c_void_p]),
+    "dad3d_encoder_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32]),
+    "dad3d_encoder_destroy": (None, [C.c_void_p]),
+    "dad3d_encoder_num_layers": (C.c_int, [C.c_void_p]),
+    "dad3d_encoder_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int32]),
+    "dad3d_encoder_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_size_t, C.c_void_p]),
+    "dad3d_encoder_set_debug": (C.c_int, [C.c_void_p, C.c_int32]),
+    "dad3d_encoder_read_activation": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t,
+                                                 C.POINTER(C.c_int32), C.c_void_p]),
 }
 
 

@@ -1,0 +1,718 @@
+// DAD-3DNet encoder (FlameRegression.forward, model_training/model/flame_regression.py:87-106) for sm_100a.
+// Host side: folded weights -> bf16 piece planes + TMA maps (create), a per-batch-size execution plan with a
+// liveness-based workspace layout (plan), and the launch loop (forward).  Device side: tile_gemm.cuh (every conv /
+// linear layer as an implicit GEMM on tcgen05) + encoder_kernels.cuh (stem, pooling, BiFPN sums, fusion concat, heads).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/dad3d.h"
+#include "common.h"
+#include "encoder_kernels.cuh"
+#include "tmap.h"
+
+using namespace dad3d;
+
+namespace {
+
+constexpr int kImg = 256;
+constexpr int kStageUnits[4] = {3, 4, 6, 3};
+constexpr int kNumFilters = 256;
+constexpr int kHeat = 68;
+constexpr int kHeatCat = 128;      // heat-map slot inside the FusionLayer concat (64-channel granularity)
+constexpr int kMlpOut = 549;       // 403 + 10 + 136
+constexpr float kLimitValue = 3.0f;
+
+struct ConvW {
+  std::string name;
+  int cout = 0, cin = 0, R = 1, S = 1;
+  int cout_pad = 0, cin_pad = 0, block_n = 0;
+  uint16_t* d_w = nullptr;      // [P][cout_pad][R*S*cin_pad] bf16 pieces
+  float* d_bias = nullptr;      // [cout_pad]
+  CUtensorMap map_b[kMaxPieces];
+};
+
+int pick_block_n(int cout) {
+  if (cout % 128 == 0) return 128;
+  if (cout % 64 == 0) return 64;
+  return 96;                                  // 68 -> 96, 549 -> 6 x 96
+}
+
+inline uint16_t host_bf16(float x) {          // round-to-nearest-even fp32 -> bf16
+  uint32_t u;
+  std::memcpy(&u, &x, 4);
+  if ((u & 0x7f800000u) == 0x7f800000u) return static_cast<uint16_t>(u >> 16);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return static_cast<uint16_t>(u >> 16);
+}
+inline float host_bf16_to_f32(uint16_t b) {
+  uint32_t u = static_cast<uint32_t>(b) << 16;
+  float f;
+  std::memcpy(&f, &u, 4);
+  return f;
+}
+
+// ---------------------------------------------------------------------------------------------- plan structures
+struct TensorInfo {
+  int N = 0, H = 0, W = 0, C = 0;
+  bool f32 = false;
+  int planes = 1;
+  size_t bytes = 0;
+  int first = 1 << 30, last = -1;
+  size_t off = 0;
+  uint8_t* ptr = nullptr;
+  std::string name;                 // debug tag (layer that produced it)
+  long long plane_elems() const { return static_cast<long long>(N) * H * W * C; }
+};
+
+enum StepKind { kStemConv, kStemPool, kConv, kFuse, kConcat, kGap, kFinalize, kHeatExport };
+
+struct Step {
+  StepKind kind;
+  // generic tensor slots
+  int in = -1, out = -1, res = -1, out_f32 = -1, in2 = -1, in3 = -1;
+  // conv
+  const ConvW* w = nullptr;
+  int stride = 1, pad = 0, relu = 0, res_mode = 0;
+  GemmMaps maps;
+  GemmGeom geom;
+  EpiConv::Params epi;
+  // fuse
+  float fw[3] = {0, 0, 0};
+  int nsrc = 0;
+};
+
+struct Plan {
+  int B = 0;
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  std::vector<TensorInfo> tensors;
+  std::vector<Step> steps;
+  int t_mlp_out = -1, t_heat = -1;
+};
+
+}  // namespace
+
+struct dad3d_encoder {
+  int device = 0;
+  int num_sms = 0;
+  int P = 3;                       // pieces per operand
+  int n_mma = 6;
+  int mma_a[kMaxMma], mma_b[kMaxMma];
+  std::map<std::string, ConvW> convs;
+  float* d_stem_w = nullptr;       // [147][64]
+  float* d_stem_b = nullptr;       // [64]
+  float bifpn_w[2][20];            // per block: w1 normalised [2][4] then w2 normalised [3][4]
+  std::unique_ptr<Plan> plan;
+  size_t ws_cache_B = 0, ws_cache_bytes = 0;
+  bool debug_keep_all = false;     // disable buffer reuse so every activation can be read back after a forward
+};
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------- plan building
+struct Builder {
+  dad3d_encoder* enc;
+  Plan* plan;
+  int B;
+
+  int tensor(int N, int H, int W, int C, bool f32 = false) {
+    TensorInfo t;
+    t.N = N; t.H = H; t.W = W; t.C = C; t.f32 = f32;
+    t.planes = f32 ? 1 : enc->P;
+    t.bytes = align_up(static_cast<size_t>(t.plane_elems()) * (f32 ? 4 : 2) * t.planes, 1024);
+    plan->tensors.push_back(t);
+    return static_cast<int>(plan->tensors.size()) - 1;
+  }
+  void touch(int t, int step) {
+    if (t < 0) return;
+    TensorInfo& ti = plan->tensors[t];
+    ti.first = std::min(ti.first, step);
+    ti.last = std::max(ti.last, step);
+  }
+  int push(Step s) {
+    const int idx = static_cast<int>(plan->steps.size());
+    for (int t : {s.in, s.out, s.res, s.out_f32, s.in2, s.in3}) touch(t, idx);
+    plan->steps.push_back(s);
+    return idx;
+  }
+  const ConvW* W(const std::string& name) {
+    auto it = enc->convs.find(name);
+    return it == enc->convs.end() ? nullptr : &it->second;
+  }
+  // conv / linear layer; returns the output tensor id (pieces) unless f32_only
+  int conv(const std::string& name, int in, int stride, int pad, bool relu, int res = -1, int res_mode = 0,
+           bool f32_out = false, bool pieces_out = true, int* f32_id = nullptr) {
+    const ConvW* w = W(name);
+    const TensorInfo ti = plan->tensors[in];
+    const int Ho = (ti.H + 2 * pad - w->R) / stride + 1;
+    const int Wo = (ti.W + 2 * pad - w->S) / stride + 1;
+    Step s;
+    std::memset(&s.maps, 0, sizeof(s.maps));
+    s.kind = kConv;
+    s.in = in;
+    s.w = w;
+    s.stride = stride;
+    s.pad = pad;
+    s.relu = relu ? 1 : 0;
+    s.res = res;
+    s.res_mode = res_mode;
+    s.out = pieces_out ? tensor(ti.N, Ho, Wo, w->cout_pad) : -1;
+    s.out_f32 = f32_out ? tensor(ti.N, Ho, Wo, w->cout_pad, true) : -1;
+    if (s.out >= 0) plan->tensors[s.out].name = name;
+    if (s.out_f32 >= 0) plan->tensors[s.out_f32].name = name + (pieces_out ? ".f32" : "");
+    if (f32_id) *f32_id = s.out_f32;
+    push(s);
+    return s.out;
+  }
+};
+
+void pick_tile(int Wo, int Ho, int* tw, int* th, int* tn) {
+  int w = 1;
+  while (w < Wo && w < kBlockM) w <<= 1;
+  *tw = w;
+  int h = 1;
+  while (h < Ho && w * h < kBlockM) h <<= 1;
+  *th = h;
+  *tn = kBlockM / (w * h);
+}
+
+int build_graph(Builder& b) {
+  const int B = b.B;
+  Plan* plan = b.plan;
+  // ---- stem: conv7x7/2 + BN + ReLU (fp32 SIMT) -> maxpool 3x3/2 -> pieces [B,64,64,64]
+  const int t_stem = b.tensor(B, kImg / 2, kImg / 2, 64, true);
+  {
+    Step s; s.kind = kStemConv; s.out_f32 = t_stem; std::memset(&s.maps, 0, sizeof(s.maps));
+    b.push(s);
+  }
+  plan->tensors[t_stem].name = "stem_conv";
+  int x = b.tensor(B, kImg / 4, kImg / 4, 64);
+  plan->tensors[x].name = "stem";
+  {
+    Step s; s.kind = kStemPool; s.in = t_stem; s.out = x; std::memset(&s.maps, 0, sizeof(s.maps));
+    b.push(s);
+  }
+  // ---- ResNet-50 stages (pytorchcv resnet50: stride on the first 1x1 of the first unit of stages 2..4)
+  int c_out[4] = {-1, -1, -1, -1};
+  auto run_stage = [&](int si, int xin) {
+    int cur = xin;
+    for (int ui = 0; ui < kStageUnits[si]; ++ui) {
+      const std::string p = "s" + std::to_string(si + 1) + "u" + std::to_string(ui + 1);
+      const int stride = (ui == 0 && si != 0) ? 2 : 1;
+      int identity = cur;
+      if (ui == 0) identity = b.conv(p + "id", cur, stride, 0, false);
+      int y = b.conv(p + "c1", cur, stride, 0, true);
+      y = b.conv(p + "c2", y, 1, 1, true);
+      cur = b.conv(p + "c3", y, 1, 0, true, identity, 1);
+    }
+    return cur;
+  };
+  for (int si = 0; si < 3; ++si) {
+    x = run_stage(si, x);
+    c_out[si] = x;
+  }
+  const int c2 = c_out[0], c3 = c_out[1], c4 = c_out[2];
+  // ---- BiFPN laterals (bifpn.py:137-145, 152-161)
+  int feat[5];
+  feat[0] = b.conv("lat3", c2, 1, 0, false);
+  feat[1] = b.conv("lat4", c3, 1, 0, false);
+  feat[2] = b.conv("lat5", c4, 1, 0, false);
+  feat[3] = b.conv("lat6", c4, 2, 1, false);
+  feat[4] = b.conv("lat7", feat[3], 2, 1, true);
+  // ---- 2 x BiFPNBlock (bifpn.py:101-131)
+  auto fuse = [&](int a, float wa, int s1, float w1, int s2, float w2) {
+    const TensorInfo ta = plan->tensors[a];
+    Step s; std::memset(&s.maps, 0, sizeof(s.maps));
+    s.kind = kFuse;
+    s.in = a; s.in2 = s1; s.in3 = s2;
+    s.nsrc = s2 >= 0 ? 3 : 2;
+    s.fw[0] = wa; s.fw[1] = w1; s.fw[2] = w2;
+    s.out = b.tensor(ta.N, ta.H, ta.W, ta.C);
+    plan->tensors[s.out].name = "fuse" + std::to_string(plan->steps.size());
+    b.push(s);
+    return s.out;
+  };
+  for (int li = 0; li < 2; ++li) {
+    const float* w1 = &b.enc->bifpn_w[li][0];     // [2][4]
+    const float* w2 = &b.enc->bifpn_w[li][8];     // [3][4]
+    const std::string p = "b" + std::to_string(li) + "_";
+    const int p3x = feat[0], p4x = feat[1], p5x = feat[2], p6x = feat[3], p7x = feat[4];
+    const int p7td = p7x;
+    const int p6td = b.conv(p + "p6td", fuse(p6x, w1[0], p7td, w1[4 + 0], -1, 0.f), 1, 0, true);
+    const int p5td = b.conv(p + "p5td", fuse(p5x, w1[1], p6td, w1[4 + 1], -1, 0.f), 1, 0, true);
+    const int p4td = b.conv(p + "p4td", fuse(p4x, w1[2], p5td, w1[4 + 2], -1, 0.f), 1, 0, true);
+    const int p3td = b.conv(p + "p3td", fuse(p3x, w1[3], p4td, w1[4 + 3], -1, 0.f), 1, 0, true);
+    const int p3out = p3td;
+    const int p4out = b.conv(p + "p4out", fuse(p4x, w2[0], p4td, w2[4 + 0], p3out, w2[8 + 0]), 1, 0, true);
+    const int p5out = b.conv(p + "p5out", fuse(p5x, w2[1], p5td, w2[4 + 1], p4out, w2[8 + 1]), 1, 0, true);
+    const int p6out = b.conv(p + "p6out", fuse(p6x, w2[2], p6td, w2[4 + 2], p5out, w2[8 + 2]), 1, 0, true);
+    const int p7out = b.conv(p + "p7out", fuse(p7x, w2[3], p7td, w2[4 + 3], p6out, w2[8 + 3]), 1, 0, true);
+    feat[0] = p3out; feat[1] = p4out; feat[2] = p5out; feat[3] = p6out; feat[4] = p7out;
+  }
+  // ---- heat-map head (flame_regression.py:22-25): 3x3 conv 256 -> 68 (+bias), kept in fp32
+  int t_heat = -1;
+  b.conv("heat", feat[0], 1, 1, false, -1, 0, /*f32_out=*/true, /*pieces_out=*/false, &t_heat);
+  plan->t_heat = t_heat;
+  // ---- FusionLayer (flame_regression.py:33-42)
+  const TensorInfo tc4 = plan->tensors[c4];
+  const int t_cat = b.tensor(B, tc4.H, tc4.W, 1024 + kHeatCat + kNumFilters);
+  plan->tensors[t_cat].name = "cat";
+  {
+    Step s; std::memset(&s.maps, 0, sizeof(s.maps));
+    s.kind = kConcat; s.in = c4; s.in2 = t_heat; s.in3 = feat[2]; s.out = t_cat;
+    b.push(s);
+  }
+  x = b.conv("fusion", t_cat, 1, 0, false, c4, 2);
+  // ---- stage 4
+  x = run_stage(3, x);
+  // ---- heads (flame_regression.py:45-59, 96-106): GAP -> [3 x Linear 2048->512 + ReLU] -> block-diagonal second layers
+  const TensorInfo tx = plan->tensors[x];
+  const int t_gap = b.tensor(1, 1, B, tx.C);
+  plan->tensors[t_gap].name = "gap";
+  {
+    Step s; std::memset(&s.maps, 0, sizeof(s.maps));
+    s.kind = kGap; s.in = x; s.out = t_gap;
+    b.push(s);
+  }
+  const int t_h = b.conv("mlp1", t_gap, 1, 0, true);
+  int t_out = -1;
+  b.conv("mlp2", t_h, 1, 0, false, -1, 0, true, false, &t_out);
+  plan->t_mlp_out = t_out;
+  {
+    Step s; std::memset(&s.maps, 0, sizeof(s.maps));
+    s.kind = kFinalize; s.in = t_out;
+    b.push(s);
+  }
+  {
+    Step s; std::memset(&s.maps, 0, sizeof(s.maps));
+    s.kind = kHeatExport; s.in = t_heat;
+    b.push(s);
+  }
+  return DAD3D_OK;
+}
+
+// first-fit offset assignment over live ranges [first, last]
+size_t assign_offsets(std::vector<TensorInfo>& ts) {
+  std::vector<int> order(ts.size());
+  for (size_t i = 0; i < ts.size(); ++i) order[i] = static_cast<int>(i);
+  std::sort(order.begin(), order.end(), [&](int a, int b) {
+    if (ts[a].first != ts[b].first) return ts[a].first < ts[b].first;
+    return ts[a].bytes > ts[b].bytes;
+  });
+  std::vector<int> placed;
+  size_t total = 0;
+  for (int id : order) {
+    TensorInfo& t = ts[id];
+    if (t.last < 0) { t.off = 0; continue; }
+    std::vector<std::pair<size_t, size_t>> busy;       // [off, off+bytes) of overlapping-lifetime tensors
+    for (int pid : placed) {
+      const TensorInfo& p = ts[pid];
+      if (p.last < t.first || p.first > t.last) continue;
+      busy.emplace_back(p.off, p.off + p.bytes);
+    }
+    std::sort(busy.begin(), busy.end());
+    size_t off = 0;
+    for (auto& iv : busy) {
+      if (off + t.bytes <= iv.first) break;
+      off = std::max(off, iv.second);
+    }
+    t.off = off;
+    total = std::max(total, off + t.bytes);
+    placed.push_back(id);
+  }
+  return total;
+}
+
+int make_plan(dad3d_encoder* enc, int B, void* ws, size_t ws_bytes, bool layout_only, size_t* need) {
+  std::unique_ptr<Plan> plan(new Plan());
+  plan->B = B;
+  Builder b{enc, plan.get(), B};
+  int rc = build_graph(b);
+  if (rc != DAD3D_OK) return rc;
+  if (enc->debug_keep_all)
+    for (auto& t : plan->tensors) { t.first = 0; t.last = 1 << 29; }
+  const size_t total = assign_offsets(plan->tensors) + 1024;
+  if (need) *need = total;
+  if (layout_only) return DAD3D_OK;
+  if (ws_bytes < total) {
+    set_error("encoder workspace too small: need " + std::to_string(total) + " bytes");
+    return DAD3D_ERR_INVALID;
+  }
+  uint8_t* base = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(ws), 1024));
+  for (auto& t : plan->tensors) t.ptr = base + t.off;
+  plan->ws = ws;
+  plan->ws_bytes = ws_bytes;
+
+  auto view = [&](int id) {
+    ActView v{nullptr, 0, 0, 0};
+    if (id < 0) return v;
+    const TensorInfo& t = plan->tensors[id];
+    v.base = reinterpret_cast<const uint16_t*>(t.ptr);
+    v.plane = t.plane_elems();
+    v.planes = t.planes;
+    v.C = t.C;
+    return v;
+  };
+  for (Step& s : plan->steps) {
+    if (s.kind != kConv) continue;
+    const TensorInfo& ti = plan->tensors[s.in];
+    const ConvW* w = s.w;
+    if (ti.C != w->cin_pad) {
+      set_error("layer " + w->name + ": input has " + std::to_string(ti.C) + " channels, weights expect " +
+                std::to_string(w->cin_pad));
+      return DAD3D_ERR_INVALID;
+    }
+    const int Ho = (ti.H + 2 * s.pad - w->R) / s.stride + 1;
+    const int Wo = (ti.W + 2 * s.pad - w->S) / s.stride + 1;
+    GemmGeom& g = s.geom;
+    std::memset(&g, 0, sizeof(g));
+    pick_tile(Wo, Ho, &g.tw, &g.th, &g.tn);
+    g.tiles_w = ceil_div(Wo, g.tw);
+    g.tiles_h = ceil_div(Ho, g.th);
+    g.tiles_n = ceil_div(ti.N, g.tn);
+    g.Wo = Wo; g.Ho = Ho; g.Nimg = ti.N;
+    g.stride = s.stride;
+    g.R = w->R; g.S = w->S; g.pad_h = s.pad; g.pad_w = s.pad;
+    g.cin_blocks = w->cin_pad / kBlockK;
+    g.block_n = w->block_n;
+    g.n_tiles = w->cout_pad / w->block_n;
+    g.nA = enc->P; g.nB = enc->P;
+    g.n_mma = enc->n_mma;
+    for (int i = 0; i < enc->n_mma; ++i) { g.mma_a[i] = enc->mma_a[i]; g.mma_b[i] = enc->mma_b[i]; }
+    g.fmt16 = 1;
+    g.stages = std::min(8, (227 * 1024 - 2048) / gemm_stage_bytes(g));
+    if (g.stages < 2) { set_error("layer " + w->name + ": pipeline does not fit shared memory"); return DAD3D_ERR_INVALID; }
+    for (int p = 0; p < enc->P; ++p) {
+      const uint64_t dims[4] = {static_cast<uint64_t>(ti.C), static_cast<uint64_t>(ti.W), static_cast<uint64_t>(ti.H),
+                                static_cast<uint64_t>(ti.N)};
+      const uint64_t strides[3] = {static_cast<uint64_t>(ti.C) * 2, static_cast<uint64_t>(ti.W) * ti.C * 2,
+                                   static_cast<uint64_t>(ti.H) * ti.W * ti.C * 2};
+      const uint32_t box[4] = {kBlockK, static_cast<uint32_t>(g.tw * s.stride), static_cast<uint32_t>(g.th * s.stride),
+                               static_cast<uint32_t>(g.tn)};
+      const uint32_t es[4] = {1, static_cast<uint32_t>(s.stride), static_cast<uint32_t>(s.stride), 1};
+      const uint16_t* basep = reinterpret_cast<const uint16_t*>(ti.ptr) + static_cast<size_t>(p) * ti.plane_elems();
+      if (!make_tmap_16bit(&s.maps.a[p], basep, 4, dims, strides, box, es)) return DAD3D_ERR_CUDA;
+      s.maps.b[p] = w->map_b[p];
+    }
+    EpiConv::Params& ep = s.epi;
+    std::memset(&ep, 0, sizeof(ep));
+    ep.bias = w->d_bias;
+    ep.relu = s.relu;
+    ep.res_mode = s.res_mode;
+    ep.res = view(s.res);
+    if (s.res >= 0 && plan->tensors[s.res].C != w->cout_pad) {
+      set_error("layer " + w->name + ": residual channel mismatch");
+      return DAD3D_ERR_INVALID;
+    }
+    if (s.out >= 0) {
+      const TensorInfo& to = plan->tensors[s.out];
+      ep.out = reinterpret_cast<uint16_t*>(to.ptr);
+      ep.out_plane = to.plane_elems();
+      ep.out_planes = to.planes;
+      ep.ld_out = to.C;
+    }
+    if (s.out_f32 >= 0) {
+      const TensorInfo& to = plan->tensors[s.out_f32];
+      ep.out_f32 = reinterpret_cast<float*>(to.ptr);
+      ep.ld_f32 = to.C;
+    }
+  }
+  enc->plan = std::move(plan);
+  return DAD3D_OK;
+}
+
+int launch_conv(const dad3d_encoder* enc, const Step& s, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    DAD3D_CUDA_OK(cudaFuncSetAttribute(tile_gemm_kernel<EpiConv>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  const GemmGeom& g = s.geom;
+  const int total = g.tiles_w * g.tiles_h * g.tiles_n * g.n_tiles;
+  const int grid = std::min(total, enc->num_sms);
+  tile_gemm_kernel<EpiConv><<<grid, kGemmThreads, gemm_smem_bytes(g), stream>>>(s.maps, g, s.epi);
+  count_launch();
+  DAD3D_CUDA_OK(cudaGetLastError());
+  return DAD3D_OK;
+}
+
+}  // namespace
+
+// =================================================================================================== C ABI
+extern "C" {
+
+int dad3d_encoder_create(dad3d_encoder** out, const dad3d_conv_weights* layers, int32_t n_layers,
+                         const float* bifpn_fusion_w_h, int32_t pieces, int32_t device) {
+  DAD3D_REQUIRE(out && layers && bifpn_fusion_w_h, "null pointer");
+  DAD3D_REQUIRE(pieces >= 1 && pieces <= 3, "pieces must be 1 (bf16), 2 (bf16x2, 3 products) or 3 (bf16x3, 6 products)");
+  DAD3D_CUDA_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  DAD3D_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("libdad3d requires an sm_100 (Blackwell) device");
+    return DAD3D_ERR_UNSUPPORTED;
+  }
+  std::unique_ptr<dad3d_encoder> enc(new dad3d_encoder());
+  enc->device = device;
+  enc->num_sms = prop.multiProcessorCount;
+  enc->P = pieces;
+  // product list, smallest terms first so they are not swamped in the fp32 accumulator
+  if (pieces == 1) {
+    enc->n_mma = 1; enc->mma_a[0] = 0; enc->mma_b[0] = 0;
+  } else if (pieces == 2) {
+    const int pa[3] = {1, 0, 0}, pb[3] = {0, 1, 0};
+    enc->n_mma = 3;
+    for (int i = 0; i < 3; ++i) { enc->mma_a[i] = pa[i]; enc->mma_b[i] = pb[i]; }
+  } else {
+    const int pa[6] = {2, 0, 1, 1, 0, 0}, pb[6] = {0, 2, 1, 0, 1, 0};
+    enc->n_mma = 6;
+    for (int i = 0; i < 6; ++i) { enc->mma_a[i] = pa[i]; enc->mma_b[i] = pb[i]; }
+  }
+  std::memcpy(enc->bifpn_w, bifpn_fusion_w_h, sizeof(enc->bifpn_w));
+
+  auto fail = [&](int code) { dad3d_encoder_destroy(enc.release()); return code; };
+  for (int li = 0; li < n_layers; ++li) {
+    const dad3d_conv_weights& L = layers[li];
+    if (!L.name || !L.weight_h || !L.bias_h || L.cout <= 0 || L.cin <= 0 || L.R <= 0 || L.S <= 0) {
+      set_error("invalid layer record " + std::to_string(li));
+      return fail(DAD3D_ERR_INVALID);
+    }
+    const std::string name(L.name);
+    if (name == "stem") {
+      if (L.cout != 64 || L.cin != 3 || L.R != 7 || L.S != 7) { set_error("stem must be 7x7 3->64"); return fail(DAD3D_ERR_INVALID); }
+      std::vector<float> w(147 * 64);
+      for (int o = 0; o < 64; ++o)
+        for (int r = 0; r < 7; ++r)
+          for (int s = 0; s < 7; ++s)
+            for (int c = 0; c < 3; ++c)       // input [cout][R][S][cin] -> [(c*7+r)*7+s][cout]
+              w[((c * 7 + r) * 7 + s) * 64 + o] = L.weight_h[((static_cast<size_t>(o) * 7 + r) * 7 + s) * 3 + c];
+      if (cudaMalloc(&enc->d_stem_w, w.size() * 4) != cudaSuccess || cudaMalloc(&enc->d_stem_b, 64 * 4) != cudaSuccess ||
+          cudaMemcpy(enc->d_stem_w, w.data(), w.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+          cudaMemcpy(enc->d_stem_b, L.bias_h, 64 * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_error("stem upload failed");
+        return fail(DAD3D_ERR_CUDA);
+      }
+      continue;
+    }
+    ConvW cw;
+    cw.name = name;
+    cw.cout = L.cout; cw.cin = L.cin; cw.R = L.R; cw.S = L.S;
+    cw.block_n = pick_block_n(L.cout);
+    cw.cout_pad = ceil_div(L.cout, cw.block_n) * cw.block_n;
+    cw.cin_pad = ceil_div(L.cin, kBlockK) * kBlockK;
+    const size_t ktot = static_cast<size_t>(L.R) * L.S * cw.cin_pad;
+    const size_t plane = static_cast<size_t>(cw.cout_pad) * ktot;
+    std::vector<uint16_t> packed(plane * pieces, 0);
+    for (int o = 0; o < L.cout; ++o)
+      for (int t = 0; t < L.R * L.S; ++t)
+        for (int c = 0; c < L.cin; ++c) {
+          float r = L.weight_h[(static_cast<size_t>(o) * L.R * L.S + t) * L.cin + c];
+          const size_t idx = static_cast<size_t>(o) * ktot + static_cast<size_t>(t) * cw.cin_pad + c;
+          for (int p = 0; p < pieces; ++p) {
+            const uint16_t h = host_bf16(r);
+            packed[p * plane + idx] = h;
+            r -= host_bf16_to_f32(h);
+          }
+        }
+    std::vector<float> bias(cw.cout_pad, 0.f);
+    for (int o = 0; o < L.cout; ++o) bias[o] = L.bias_h[o];
+    if (cudaMalloc(&cw.d_w, packed.size() * 2) != cudaSuccess || cudaMalloc(&cw.d_bias, bias.size() * 4) != cudaSuccess ||
+        cudaMemcpy(cw.d_w, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(cw.d_bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+      set_error("weight upload failed for " + name);
+      cudaFree(cw.d_w); cudaFree(cw.d_bias);
+      return fail(DAD3D_ERR_CUDA);
+    }
+    for (int p = 0; p < pieces; ++p) {
+      const uint64_t dims[2] = {static_cast<uint64_t>(ktot), static_cast<uint64_t>(cw.cout_pad)};
+      const uint64_t strides[1] = {static_cast<uint64_t>(ktot) * 2};
+      const uint32_t box[2] = {kBlockK, static_cast<uint32_t>(cw.block_n)};
+      if (!make_tmap_16bit(&cw.map_b[p], cw.d_w + p * plane, 2, dims, strides, box, nullptr)) {
+        cudaFree(cw.d_w); cudaFree(cw.d_bias);
+        return fail(DAD3D_ERR_CUDA);
+      }
+    }
+    enc->convs[name] = cw;
+  }
+  // every layer the graph needs must be present
+  {
+    std::vector<std::string> need = {"lat3", "lat4", "lat5", "lat6", "lat7", "heat", "fusion", "mlp1", "mlp2"};
+    for (int si = 0; si < 4; ++si)
+      for (int ui = 0; ui < kStageUnits[si]; ++ui) {
+        const std::string p = "s" + std::to_string(si + 1) + "u" + std::to_string(ui + 1);
+        need.push_back(p + "c1"); need.push_back(p + "c2"); need.push_back(p + "c3");
+        if (ui == 0) need.push_back(p + "id");
+      }
+    for (int li = 0; li < 2; ++li)
+      for (const char* n : {"p6td", "p5td", "p4td", "p3td", "p4out", "p5out", "p6out", "p7out"})
+        need.push_back("b" + std::to_string(li) + "_" + n);
+    for (auto& n : need)
+      if (!enc->convs.count(n)) { set_error("missing layer weights: " + n); return fail(DAD3D_ERR_INVALID); }
+    if (!enc->d_stem_w) { set_error("missing layer weights: stem"); return fail(DAD3D_ERR_INVALID); }
+  }
+  *out = enc.release();
+  return DAD3D_OK;
+}
+
+void dad3d_encoder_destroy(dad3d_encoder* enc) {
+  if (!enc) return;
+  for (auto& kv : enc->convs) {
+    cudaFree(kv.second.d_w);
+    cudaFree(kv.second.d_bias);
+  }
+  cudaFree(enc->d_stem_w);
+  cudaFree(enc->d_stem_b);
+  delete enc;
+}
+
+size_t dad3d_encoder_workspace_bytes(dad3d_encoder* enc, int32_t B) {
+  if (!enc || B <= 0) return 0;
+  if (enc->ws_cache_B == static_cast<size_t>(B)) return enc->ws_cache_bytes;
+  size_t need = 0;
+  if (make_plan(enc, B, nullptr, 0, true, &need) != DAD3D_OK) return 0;
+  enc->ws_cache_B = B;
+  enc->ws_cache_bytes = need;
+  return need;
+}
+
+int dad3d_encoder_forward(dad3d_encoder* enc, const float* images_d, int32_t B, float* params_d, float* landmarks_d,
+                          float* heatmap_d, void* workspace_d, size_t workspace_bytes, dad3d_stream stream_) {
+  DAD3D_REQUIRE(enc, "null handle");
+  if (B == 0) return DAD3D_OK;
+  DAD3D_REQUIRE(B > 0 && images_d && params_d && landmarks_d && workspace_d, "null pointer / batch");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!enc->plan || enc->plan->B != B || enc->plan->ws != workspace_d || enc->plan->ws_bytes != workspace_bytes) {
+    int rc = make_plan(enc, B, workspace_d, workspace_bytes, false, nullptr);
+    if (rc != DAD3D_OK) return rc;
+  }
+  const Plan& plan = *enc->plan;
+  auto T = [&](int id) -> const TensorInfo& { return plan.tensors[id]; };
+  auto view = [&](int id) {
+    const TensorInfo& t = T(id);
+    return ActView{reinterpret_cast<const uint16_t*>(t.ptr), t.plane_elems(), t.planes, t.C};
+  };
+  for (const Step& s : plan.steps) {
+    switch (s.kind) {
+      case kStemConv: {
+        const TensorInfo& to = T(s.out_f32);
+        dim3 grid(ceil_div(to.W, kStemTile), ceil_div(to.H, kStemTile), B);
+        static bool stem_configured = false;
+        if (!stem_configured) {
+          DAD3D_CUDA_OK(cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemSmemBytes));
+          stem_configured = true;
+        }
+        stem_conv_kernel<<<grid, 256, kStemSmemBytes, stream>>>(images_d, enc->d_stem_w, enc->d_stem_b, kImg, kImg,
+                                                   reinterpret_cast<float*>(to.ptr));
+        count_launch();
+        break;
+      }
+      case kStemPool: {
+        const TensorInfo& ti = T(s.in);
+        const TensorInfo& to = T(s.out);
+        const long long total = static_cast<long long>(B) * to.H * to.W * 8;
+        stem_pool_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+            reinterpret_cast<const float*>(ti.ptr), B, ti.H, ti.W, reinterpret_cast<uint16_t*>(to.ptr), to.plane_elems(),
+            to.planes);
+        count_launch();
+        break;
+      }
+      case kConv: {
+        int rc = launch_conv(enc, s, stream);
+        if (rc != DAD3D_OK) return rc;
+        break;
+      }
+      case kFuse: {
+        const TensorInfo& to = T(s.out);
+        FuseSrc f0{view(s.in), T(s.in).H, T(s.in).W, s.fw[0]};
+        FuseSrc f1{view(s.in2), T(s.in2).H, T(s.in2).W, s.fw[1]};
+        FuseSrc f2 = f1;
+        if (s.nsrc == 3) f2 = FuseSrc{view(s.in3), T(s.in3).H, T(s.in3).W, s.fw[2]};
+        const long long total = static_cast<long long>(to.N) * to.H * to.W * (to.C / 8);
+        bifpn_fuse_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+            f0, f1, f2, s.nsrc, to.N, to.H, to.W, to.C, reinterpret_cast<uint16_t*>(to.ptr), to.plane_elems(), to.planes);
+        count_launch();
+        break;
+      }
+      case kConcat: {
+        const TensorInfo& to = T(s.out);
+        const TensorInfo& th = T(s.in2);
+        const long long total = static_cast<long long>(to.N) * to.H * to.W * (to.C / 8);
+        fusion_concat_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+            view(s.in), T(s.in).C, reinterpret_cast<const float*>(th.ptr), th.H, th.W, th.C, kHeat, kHeatCat, view(s.in3),
+            T(s.in3).C, to.N, to.H, to.W, reinterpret_cast<uint16_t*>(to.ptr), to.plane_elems(), to.planes);
+        count_launch();
+        break;
+      }
+      case kGap: {
+        const TensorInfo& ti = T(s.in);
+        const TensorInfo& to = T(s.out);
+        const int total = B * (ti.C / 8);
+        gap_kernel<<<ceil_div(total, 128), 128, 0, stream>>>(view(s.in), B, ti.H * ti.W, ti.C,
+                                                             reinterpret_cast<uint16_t*>(to.ptr), to.plane_elems(), to.planes);
+        count_launch();
+        break;
+      }
+      case kFinalize: {
+        const TensorInfo& ti = T(s.in);
+        head_finalize_kernel<<<ceil_div(B * kMlpOut, 256), 256, 0, stream>>>(reinterpret_cast<const float*>(ti.ptr), ti.C, B,
+                                                                            kLimitValue, params_d, landmarks_d);
+        count_launch();
+        break;
+      }
+      case kHeatExport: {
+        if (!heatmap_d) break;
+        const TensorInfo& ti = T(s.in);
+        const long long total = static_cast<long long>(B) * kHeat * ti.H * ti.W;
+        heatmap_export_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+            reinterpret_cast<const float*>(ti.ptr), ti.C, B, ti.H * ti.W, kHeat, heatmap_d);
+        count_launch();
+        break;
+      }
+    }
+  }
+  DAD3D_CUDA_OK(cudaGetLastError());
+  return DAD3D_OK;
+}
+
+// ---- test hooks: keep every activation alive, read one back as fp32 NHWC (channels padded as stored)
+int dad3d_encoder_set_debug(dad3d_encoder* enc, int32_t keep_all) {
+  DAD3D_REQUIRE(enc, "null handle");
+  enc->debug_keep_all = keep_all != 0;
+  enc->plan.reset();
+  enc->ws_cache_B = 0;
+  return DAD3D_OK;
+}
+
+int dad3d_encoder_read_activation(dad3d_encoder* enc, const char* name, float* out_d, size_t capacity_floats,
+                                  int32_t* dims4, dad3d_stream stream_) {
+  DAD3D_REQUIRE(enc && name && dims4, "null pointer");
+  DAD3D_REQUIRE(enc->plan, "no forward has run yet");
+  for (const TensorInfo& t : enc->plan->tensors) {
+    if (t.name != name) continue;
+    dims4[0] = t.N; dims4[1] = t.H; dims4[2] = t.W; dims4[3] = t.C;
+    const size_t n = static_cast<size_t>(t.plane_elems());
+    if (!out_d) return DAD3D_OK;
+    DAD3D_REQUIRE(capacity_floats >= n, "output buffer too small");
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (t.f32) {
+      DAD3D_CUDA_OK(cudaMemcpyAsync(out_d, t.ptr, n * 4, cudaMemcpyDeviceToDevice, stream));
+    } else {
+      ActView v{reinterpret_cast<const uint16_t*>(t.ptr), t.plane_elems(), t.planes, t.C};
+      pieces_to_f32_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(v, static_cast<long long>(n), out_d);
+      count_launch();
+      DAD3D_CUDA_OK(cudaGetLastError());
+    }
+    return DAD3D_OK;
+  }
+  set_error(std::string("no activation named ") + name);
+  return DAD3D_ERR_INVALID;
+}
+
+int dad3d_encoder_num_layers(const dad3d_encoder* enc) { return enc ? static_cast<int>(enc->convs.size()) + 1 : 0; }
+
+}  // extern "C"

@@ -127,11 +127,14 @@ struct EpiConv {
 // Block = 16x16 output pixels; thread = one pixel, 64 accumulators; weights [147][64] and the 37x37x3 patch in smem.
 constexpr int kStemTile = 16;
 constexpr int kStemPatch = kStemTile * 2 + 5;    // 37
+constexpr int kStemSmemBytes = (147 * 64 + 3 * kStemPatch * (kStemPatch + 1)) * 4;
 __global__ void __launch_bounds__(256)
 stem_conv_kernel(const float* __restrict__ img, const float* __restrict__ w /*[147][64]*/, const float* __restrict__ bias,
                  int H, int W, float* __restrict__ out) {
-  __shared__ float s_w[147 * 64];
-  __shared__ float s_in[3][kStemPatch][kStemPatch + 1];
+  extern __shared__ float stem_smem[];            // kStemSmemBytes of dynamic shared memory
+  float* s_w = stem_smem;                                                       // [147][64]
+  float (*s_in)[kStemPatch][kStemPatch + 1] =
+      reinterpret_cast<float (*)[kStemPatch][kStemPatch + 1]>(stem_smem + 147 * 64);   // [3][37][38]
   const int Ho = H / 2, Wo = W / 2;
   const int b = blockIdx.z;
   const int oy0 = blockIdx.y * kStemTile, ox0 = blockIdx.x * kStemTile;
@@ -284,10 +287,8 @@ __global__ void fusion_concat_kernel(ActView x, int Cx, const float* __restrict_
         const float v01 = __ldg(&heat[((b * Hh + y0) * Wh + x1) * ldh + ch]);
         const float v10 = __ldg(&heat[((b * Hh + y1) * Wh + x0) * ldh + ch]);
         const float v11 = __ldg(&heat[((b * Hh + y1) * Wh + x1) * ldh + ch]);
-        const float top = v00 + (v01 - v00) * lx;          // same lerp form ATen's upsample_bilinear2d uses:
-        const float bot = v10 + (v11 - v10) * lx;          //   (1-l)*a + l*b evaluated as below
+        // same evaluation order as ATen's upsample_bilinear2d: h0l*(w0l*v00 + w1l*v01) + h1l*(w0l*v10 + w1l*v11)
         const float val = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
-        (void)top; (void)bot;
         r = 1.f / (1.f + expf(-val));
       }
       v[j] = r;
@@ -332,6 +333,12 @@ __global__ void head_finalize_kernel(const float* __restrict__ mlp_out, int ld, 
   if (j < 403) params[static_cast<size_t>(b) * 413 + j] = tanhf(v) * limit;
   else if (j < 413) params[static_cast<size_t>(b) * 413 + j] = v;
   else landmarks[static_cast<size_t>(b) * 136 + (j - 413)] = fmaxf(v, 0.f);
+}
+
+// test hook: sum the piece planes back to fp32
+__global__ void pieces_to_f32_kernel(ActView a, long long n, float* __restrict__ out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = act_load(a, i);
 }
 
 // heat-map NHWC fp32 [B,HW,ld] -> NCHW fp32 [B,68,HW] (the reference's OUTPUT_LANDMARKS_HEATMAP layout)

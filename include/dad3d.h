@@ -87,6 +87,50 @@ DAD3D_API int dad3d_gather_landmarks_bary(const float* src_d, int32_t B, int32_t
                                 const int32_t* tri_idx_d, const float* bary_d, int32_t L, float* out_d,
                                 dad3d_stream stream);
 
+/* ---- DAD-3DNet encoder ---------------------------------------------------------------------------------------------
+ * Replaces the TorchScript module the reference's predictor runs (predictor.py:72,97-100), i.e.
+ * FlameRegression.forward (model_training/model/flame_regression.py:87-106): pytorchcv ResNet-50 stages -> BiFPN(256) ->
+ * heat-map head -> FusionLayer -> stage 4 -> three MLP heads.
+ *
+ * Weights arrive BN-folded, one record per GEMM-able layer, fp32, laid out [cout][R][S][cin] (channels-last taps).
+ * Layer names (the folding itself is host-side Python, dad_3dheads_b200/encoder.py, from the reference's state_dict):
+ *   "stem" (7x7 3->64)                       encoder.model.init_block.conv
+ *   "s{1..4}u{k}c{1,2,3}", "s{i}u1id"        encoder.model.stage{i}.unit{k}.body.conv{1,2,3} / .identity_conv
+ *   "lat3".."lat7"                           bifpn.p3 .. bifpn.p7
+ *   "b{0,1}_{p6td,p5td,p4td,p3td,p4out,p5out,p6out,p7out}"   bifpn.bifpn.{0,1}.<node> (depthwise scale, pointwise, BN folded)
+ *   "heat"                                   head.heatmap (3x3 256->68 + bias)
+ *   "fusion"                                 fusion_layer.conv1x1 with K laid out [x 1024 | heat 68 + 60 zero | p5 256]
+ *   "mlp1" (2048 -> 3x512)  "mlp2" (block-diagonal 1536 -> 403|10|136)   {shape,pose,landmarks}.logit_image.{0,3}
+ * bifpn_fusion_w_h: [2][20] = per BiFPN block the normalised fusion weights relu(w)/sum + 1e-4, w1 [2][4] then w2 [3][4]
+ *   (bifpn.py:105-108).
+ * pieces selects the arithmetic: 1 = plain bf16 operands (1 tensor-core product, throughput mode),
+ *   2 = bf16 hi/lo (3 products, ~1e-5 relative), 3 = bf16 three-way split (6 products, fp32-class: the parity mode). */
+typedef struct dad3d_conv_weights {
+  const char* name;
+  const float* weight_h;     /* [cout][R][S][cin] */
+  const float* bias_h;       /* [cout] */
+  int32_t cout, cin, R, S;
+} dad3d_conv_weights;
+
+DAD3D_API int dad3d_encoder_create(dad3d_encoder** out, const dad3d_conv_weights* layers, int32_t n_layers,
+                                   const float* bifpn_fusion_w_h, int32_t pieces, int32_t device);
+DAD3D_API void dad3d_encoder_destroy(dad3d_encoder* enc);
+DAD3D_API int dad3d_encoder_num_layers(const dad3d_encoder* enc);
+DAD3D_API size_t dad3d_encoder_workspace_bytes(dad3d_encoder* enc, int32_t B);
+/* images_d [B,3,256,256] NCHW fp32 (already normalised, predictor.py:195-203) ->
+ *   params_d [B,413] (OUTPUT_3DMM_PARAMS), landmarks_d [B,68,2] (OUTPUT_2D_LANDMARKS, in [0,1] image units),
+ *   heatmap_d [B,68,64,64] NCHW fp32 or NULL (OUTPUT_LANDMARKS_HEATMAP). */
+DAD3D_API int dad3d_encoder_forward(dad3d_encoder* enc, const float* images_d, int32_t B, float* params_d,
+                                    float* landmarks_d, float* heatmap_d, void* workspace_d, size_t workspace_bytes,
+                                    dad3d_stream stream);
+
+/* test hooks: keep_all != 0 disables workspace reuse so that, after a forward, any activation can be read back by the
+ * name of the layer that produced it ("stem", "s2u1c3", "b1_p4out", "cat", "fusion", "gap", "heat", "mlp2" ...) as fp32
+ * NHWC with channels padded as stored; dims4 receives [N,H,W,C] (pass out_d = NULL to query the shape only). */
+DAD3D_API int dad3d_encoder_set_debug(dad3d_encoder* enc, int32_t keep_all);
+DAD3D_API int dad3d_encoder_read_activation(dad3d_encoder* enc, const char* name, float* out_d, size_t capacity_floats,
+                                            int32_t* dims4, dad3d_stream stream);
+
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 DAD3D_API unsigned long long dad3d_launch_count(void);
 

@@ -1,0 +1,82 @@
+"""Test-only CPU executor of the FOLDED layer list (dad_3dheads_b200.encoder.fold_state_dict) following the same graph as
+csrc/encoder.cu.  Two uses: (1) on CPU it pins the folding (BN fold, K layouts, block-diagonal heads, fusion scalars)
+against the oracle; (2) on the GPU box it gives per-layer expected activations, by the library's layer names, so a
+mismatch is localised to one kernel."""
+from typing import Dict
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+STAGE_UNITS = (3, 4, 6, 3)
+
+
+def run_folded(x: torch.Tensor, layers, fusion_w: np.ndarray, dtype=torch.float64) -> Dict[str, torch.Tensor]:
+    """x [B,3,256,256] -> dict layer-name -> NCHW activation (true channel counts), plus 'params', 'landmarks', 'heat'."""
+    L = {n: (torch.from_numpy(w).to(dtype).permute(0, 3, 1, 2).contiguous(), torch.from_numpy(b).to(dtype))
+         for n, w, b in layers}
+    acts: Dict[str, torch.Tensor] = {}
+
+    def conv(name, t, stride=1, pad=0, relu=False, res=None, mul=None):
+        w, b = L[name]
+        y = F.conv2d(t, w, b, stride, pad)
+        if res is not None:
+            y = y + res
+        if mul is not None:
+            y = y * mul
+        if relu:
+            y = F.relu(y)
+        acts[name] = y
+        return y
+
+    x = x.to(dtype)
+    y = conv("stem", x, 2, 3, True)
+    acts["stem_conv"] = y
+    y = F.max_pool2d(y, 3, 2, 1)
+    acts["stem"] = y
+
+    def stage(si, t):
+        for ui in range(STAGE_UNITS[si]):
+            p = f"s{si + 1}u{ui + 1}"
+            stride = 2 if (ui == 0 and si != 0) else 1
+            ident = conv(p + "id", t, stride) if ui == 0 else t
+            u = conv(p + "c1", t, stride, 0, True)
+            u = conv(p + "c2", u, 1, 1, True)
+            t = conv(p + "c3", u, 1, 0, True, res=ident)
+        return t
+
+    c2 = stage(0, y)
+    c3 = stage(1, c2)
+    c4 = stage(2, c3)
+    feat = [conv("lat3", c2), conv("lat4", c3), conv("lat5", c4), conv("lat6", c4, 2, 1)]
+    feat.append(conv("lat7", feat[3], 2, 1, True))
+    near = lambda t, ref: F.interpolate(t, size=ref.shape[2:])
+    for li in range(2):
+        w1 = fusion_w[li, :8].reshape(2, 4).astype(np.float64)
+        w2 = fusion_w[li, 8:].reshape(3, 4).astype(np.float64)
+        p3x, p4x, p5x, p6x, p7x = feat
+        p = f"b{li}_"
+        p7td = p7x
+        p6td = conv(p + "p6td", w1[0, 0] * p6x + w1[1, 0] * near(p7td, p6x), relu=True)
+        p5td = conv(p + "p5td", w1[0, 1] * p5x + w1[1, 1] * near(p6td, p5x), relu=True)
+        p4td = conv(p + "p4td", w1[0, 2] * p4x + w1[1, 2] * near(p5td, p4x), relu=True)
+        p3td = conv(p + "p3td", w1[0, 3] * p3x + w1[1, 3] * near(p4td, p3x), relu=True)
+        p4o = conv(p + "p4out", w2[0, 0] * p4x + w2[1, 0] * p4td + w2[2, 0] * near(p3td, p4x), relu=True)
+        p5o = conv(p + "p5out", w2[0, 1] * p5x + w2[1, 1] * p5td + w2[2, 1] * near(p4o, p5x), relu=True)
+        p6o = conv(p + "p6out", w2[0, 2] * p6x + w2[1, 2] * p6td + w2[2, 2] * near(p5o, p6x), relu=True)
+        p7o = conv(p + "p7out", w2[0, 3] * p7x + w2[1, 3] * p7td + w2[2, 3] * near(p6o, p7x), relu=True)
+        feat = [p3td, p4o, p5o, p6o, p7o]
+    heat = conv("heat", feat[0], 1, 1)
+    hm = F.interpolate(heat, size=c4.shape[2:], mode="bilinear", align_corners=True).sigmoid()
+    pad = torch.zeros(hm.shape[0], 128 - hm.shape[1], *hm.shape[2:], dtype=dtype)
+    cat = torch.cat([c4, hm, pad, feat[2]], 1)
+    acts["cat"] = cat
+    f = conv("fusion", cat, mul=c4)
+    s4 = stage(3, f)
+    gap = F.adaptive_avg_pool2d(s4, 1)
+    acts["gap"] = gap
+    h = conv("mlp1", gap, relu=True)
+    o = conv("mlp2", h).flatten(1)
+    acts["params"] = torch.cat([torch.tanh(o[:, :403]) * 3.0, o[:, 403:413]], 1)
+    acts["landmarks"] = F.relu(o[:, 413:549]).reshape(-1, 68, 2)
+    return acts
