@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""Headline benchmark: heads/sec at 256x256 (image -> 413 FLAME params -> 5023x3 vertices -> projected landmarks).
+
+    python bench.py --gpus N --steps K --warmup W                 # this repo (B200-native path)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's own algorithm on the host CPU cores
+
+Workload at N=1 = BASELINE.json configs[1]: batch 64 of 256x256 synthetic (seeded randn, already-normalised) images,
+random-init weights of the DAD-3DNet architecture, encoder in the fp32-class mode (three-way bf16 split, 6 tensor-core
+products per tile) + FLAME decode (fp16 hi/lo 3-product blend) + projection + 445-landmark gather.  N>1: every rank
+runs the same per-GPU batch on its own shard (weak scaling); constants are broadcast from rank 0 over NCCL at start-up
+and per-step outputs (params, vertices, landmarks) are all-gathered inside the timed region.
+
+One JSON line on stdout (rank 0).  `value` = whole-job heads/s with inputs resident in HBM; `e2e` = the same through
+FaceMeshPredictor.predict_batch with pinned HOST inputs and host-side results (H2D + D2H inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "heads/sec @256x256 (5023-vert FLAME)"
+UNIT = "heads/s"
+PER_GPU_BATCH = 64
+FLOPS_PER_IMAGE_ENCODER = 2 * 7_559_801_344        # SURVEY §8(d), analytic
+FLOPS_PER_HEAD_BLEND = 13_140_168                  # 2*15069*(400+36), as written in the reference
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d.get("hbm_gbs", 6650.0), "bf16_tflops": d.get("bf16_tflops", 1590.0),
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", 1400.0), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int = 0):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 7:
+                    self.samples.append(f)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        sm = sorted(int(float(s[0])) for s in self.samples if s[0].replace(".", "").isdigit())
+        mx = [int(float(s[1])) for s in self.samples if s[1].replace(".", "").isdigit()]
+        reasons = []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for i, n in enumerate(names):
+            if any(s[3 + i].lower().startswith("active") for s in self.samples):
+                reasons.append(n)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    """The reference's own algorithm (oracle restatement, kind "port": the reference package cannot be imported offline,
+    see DESIGN.md) on the box's host cores, same metric/config, each step a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from dad_3dheads_b200.encoder_weights import synthetic_state_dict
+    from oracle.predictor_oracle import PredictorOracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample = 8                                          # images per step (bounded sample of the 64-image batch)
+    po = PredictorOracle(synthetic_state_dict(0))
+    x = torch.randn(sample, 3, 256, 256, generator=torch.Generator().manual_seed(0))
+    for _ in range(args.warmup):
+        po.predict_batch(x)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        po.predict_batch(x)
+    dt = time.perf_counter() - t0
+    val = sample * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": "configs[1]: batch=64 256x256 encoder+FLAME decode, fp32", "per_gpu_batch": PER_GPU_BATCH,
+                       "sample_per_step": sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{sample} images/step x {args.steps} steps, torch CPU fp32 oracle restatement"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from dad_3dheads_b200 import _lib
+    from dad_3dheads_b200.encoder_weights import synthetic_state_dict
+    from dad_3dheads_b200.flame import load_flame_static
+    from dad_3dheads_b200.predictor import DEFAULT_CONFIG, FaceMeshPredictor
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU path)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    distributed = world > 1
+    if distributed:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- constants: rank 0 owns them, everyone else receives them over NCCL (north_star: "NCCL broadcast of the bases")
+    sd = synthetic_state_dict(0)
+    static = load_flame_static()
+    if distributed:
+        from dad_3dheads_b200.distributed import broadcast_flame_static, broadcast_state_dict
+        sd = broadcast_state_dict(sd, dev)
+        static = broadcast_flame_static(static, dev)
+    pred = FaceMeshPredictor(dict(DEFAULT_CONFIG), cuda_id=local_rank, state_dict=sd, precision=args.precision)
+    if distributed:
+        pred.head_mesh = type(pred.head_mesh)(pred.flame_constants, cuda_id=local_rank, static=static)
+
+    B = args.batch
+    g = torch.Generator().manual_seed(1234 + rank)
+    x_host = torch.randn(B, 3, 256, 256, generator=g).pin_memory()
+    x_dev = x_host.to(dev)
+    subset = "445"
+
+    gathered = {}
+
+    def step_device():
+        out = pred.predict_batch(x_dev, landmark_subset=subset)
+        if distributed:
+            from dad_3dheads_b200.distributed import all_gather_outputs
+            all_gather_outputs(out, ("3dmm_params", "3d_vertices", "landmarks_445"), gathered)
+        return out
+
+    host_out = {}
+
+    def step_e2e():
+        out = pred.predict_batch(x_host, landmark_subset=subset)       # H2D of the images happens in here
+        for k in ("3dmm_params", "points", "3d_vertices", "landmarks_445"):
+            if k not in host_out:
+                host_out[k] = torch.empty(out[k].shape, dtype=out[k].dtype).pin_memory()
+            host_out[k].copy_(out[k], non_blocking=True)
+        torch.cuda.current_stream().synchronize()                      # the caller holds host results
+        return out
+
+    def timed(fn, steps, profile=False):
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if profile:
+            pred.model.set_profile(True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        prof = pred.model.profile_read() if profile else None
+        if profile:
+            pred.model.set_profile(False)
+        if distributed:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.barrier()
+            ms = float(t.item())
+        return ms, prof
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = _lib.launch_count()
+    if sampler:
+        sampler.start()
+    ms_total, prof = timed(step_device, args.steps, profile=True)
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+
+    for _ in range(2):
+        step_e2e()
+    ms_e2e, _ = timed(step_e2e, args.steps)
+
+    if rank == 0:
+        peaks = _peaks()
+        heads = B * world * args.steps
+        value = heads / (ms_total * 1e-3)
+        e2e_value = heads / (ms_e2e * 1e-3)
+        gemm_ms, gemm_launches, useful_flops = prof
+        products = {"fp32": 6, "bf16x3": 6, "bf16x2": 3, "bf16": 1}[args.precision]
+        achieved = useful_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+        peak = peaks["bf16_tflops_sustained"]
+        h2d = x_host.numel() * 4
+        d2h = sum(v.numel() * v.element_size() for v in host_out.values())
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp32 (bf16x3 split operands, fp32 accumulate)" if products == 6 else args.precision,
+            "data": "synthetic",
+            "config": {"workload": "configs[1]: batch=64 256x256 encoder+FLAME decode, fp32, per GPU",
+                       "per_gpu_batch": B, "global_batch": B * world, "encoder_precision": args.precision,
+                       "decode": "fp16 hi/lo 3-product blend + LBS + projection + 445-landmark gather",
+                       "parallelism": f"dp{world} (batch sharded, NCCL bcast constants + all-gather outputs)" if distributed
+                       else "single GPU",
+                       "l2": "no explicit flush: per-step working set (50 MB input + >1 GB activations) exceeds the 126 MB L2"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps, "api": "FaceMeshPredictor.predict_batch (pinned host in/out)"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"kernel": "tile_gemm_kernel<EpiConv> (all conv/linear layers, tcgen05)", "bound": "tensor",
+                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+                         "traffic": None, "peak_source": peaks["source"] + " bf16 dense, sustained",
+                         "products_per_mac": products, "executed_tflops": achieved * products,
+                         "frac_executed": achieved * products / peak if peak else None,
+                         "kernel_ms_per_step": gemm_ms / args.steps, "launches_per_step": gemm_launches / args.steps,
+                         "share_of_step": gemm_ms / ms_total if ms_total else None,
+                         "algorithmic_gflop_per_head": useful_flops / heads * world / 1e9 if heads else None},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(sd, static)
+        print(json.dumps(line), flush=True)
+    if distributed:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline(sd, static):
+    """The oracle ("port" of the reference algorithm) timed on this box's host cores on a bounded sample."""
+    import torch
+    from oracle.predictor_oracle import PredictorOracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    po = PredictorOracle(sd, static=static)
+    sample = 8
+    x = torch.randn(sample, 3, 256, 256, generator=torch.Generator().manual_seed(0))
+    po.predict_batch(x)
+    reps = 0
+    t0 = time.perf_counter()
+    while reps < 3 or (time.perf_counter() - t0 < 10.0 and reps < 40):
+        po.predict_batch(x)
+        reps += 1
+    dt = time.perf_counter() - t0
+    return {"value": sample * reps / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{reps} passes of {sample} images (encoder + FLAME decode + projection), torch {torch.__version__} "
+                      f"CPU fp32, {cores} threads"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="images per GPU per step")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16x2", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

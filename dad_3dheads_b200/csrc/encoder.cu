@@ -102,7 +102,8 @@ struct dad3d_encoder {
   int num_sms = 0;
   int P = 3;                       // pieces per operand
   int n_mma = 6;
-  int mma_a[kMaxMma], mma_b[kMaxMma];
+  int n_acc = 2;
+  int mma_a[kMaxMma], mma_b[kMaxMma], mma_acc[kMaxMma];
   std::map<std::string, ConvW> convs;
   float* d_stem_w = nullptr;       // [147][64]
   float* d_stem_b = nullptr;       // [64]
@@ -110,6 +111,12 @@ struct dad3d_encoder {
   std::unique_ptr<Plan> plan;
   size_t ws_cache_B = 0, ws_cache_bytes = 0;
   bool debug_keep_all = false;     // disable buffer reuse so every activation can be read back after a forward
+  // live profiling of the dominant kernel (bench.py roofline): CUDA events around every tile_gemm launch
+  bool profile = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+  size_t prof_used = 0;
+  double prof_flops = 0.0;         // algorithmic (useful, unpadded, one-product) FLOPs of the recorded launches
+  double prof_bytes = 0.0;         // algorithmic HBM bytes of the recorded launches (inputs + weights + outputs once)
 };
 
 namespace {
@@ -383,7 +390,8 @@ int make_plan(dad3d_encoder* enc, int B, void* ws, size_t ws_bytes, bool layout_
     g.n_tiles = w->cout_pad / w->block_n;
     g.nA = enc->P; g.nB = enc->P;
     g.n_mma = enc->n_mma;
-    for (int i = 0; i < enc->n_mma; ++i) { g.mma_a[i] = enc->mma_a[i]; g.mma_b[i] = enc->mma_b[i]; }
+    g.n_acc = enc->n_acc;
+    for (int i = 0; i < enc->n_mma; ++i) { g.mma_a[i] = enc->mma_a[i]; g.mma_b[i] = enc->mma_b[i]; g.mma_acc[i] = enc->mma_acc[i]; }
     g.fmt16 = 1;
     g.stages = std::min(8, (227 * 1024 - 2048) / gemm_stage_bytes(g));
     if (g.stages < 2) { set_error("layer " + w->name + ": pipeline does not fit shared memory"); return DAD3D_ERR_INVALID; }
@@ -426,7 +434,16 @@ int make_plan(dad3d_encoder* enc, int B, void* ws, size_t ws_bytes, bool layout_
   return DAD3D_OK;
 }
 
-int launch_conv(const dad3d_encoder* enc, const Step& s, cudaStream_t stream) {
+double conv_useful_flops(const Step& s) {
+  const ConvW* w = s.w;
+  const GemmGeom& g = s.geom;
+  double cin = w->cin, cout = w->cout;
+  if (w->name == "fusion") cin -= 60;                       // zero columns that pad the heat-map slot
+  if (w->name == "mlp2") cin /= 3.0;                        // block-diagonal: each output sees one 512-wide block
+  return 2.0 * g.Nimg * g.Ho * g.Wo * cout * cin * w->R * w->S;
+}
+
+int launch_conv(dad3d_encoder* enc, const Step& s, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
     DAD3D_CUDA_OK(cudaFuncSetAttribute(tile_gemm_kernel<EpiConv>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -435,8 +452,21 @@ int launch_conv(const dad3d_encoder* enc, const Step& s, cudaStream_t stream) {
   const GemmGeom& g = s.geom;
   const int total = g.tiles_w * g.tiles_h * g.tiles_n * g.n_tiles;
   const int grid = std::min(total, enc->num_sms);
+  std::pair<cudaEvent_t, cudaEvent_t>* ev = nullptr;
+  if (enc->profile) {
+    if (enc->prof_used == enc->prof_events.size()) {
+      cudaEvent_t a, b;
+      DAD3D_CUDA_OK(cudaEventCreate(&a));
+      DAD3D_CUDA_OK(cudaEventCreate(&b));
+      enc->prof_events.emplace_back(a, b);
+    }
+    ev = &enc->prof_events[enc->prof_used++];
+    enc->prof_flops += conv_useful_flops(s);
+    DAD3D_CUDA_OK(cudaEventRecord(ev->first, stream));
+  }
   tile_gemm_kernel<EpiConv><<<grid, kGemmThreads, gemm_smem_bytes(g), stream>>>(s.maps, g, s.epi);
   count_launch();
+  if (ev) DAD3D_CUDA_OK(cudaEventRecord(ev->second, stream));
   DAD3D_CUDA_OK(cudaGetLastError());
   return DAD3D_OK;
 }
@@ -463,15 +493,15 @@ int dad3d_encoder_create(dad3d_encoder** out, const dad3d_conv_weights* layers, 
   enc->P = pieces;
   // product list, smallest terms first so they are not swamped in the fp32 accumulator
   if (pieces == 1) {
-    enc->n_mma = 1; enc->mma_a[0] = 0; enc->mma_b[0] = 0;
+    enc->n_mma = 1; enc->n_acc = 1; enc->mma_a[0] = 0; enc->mma_b[0] = 0; enc->mma_acc[0] = 0;
   } else if (pieces == 2) {
-    const int pa[3] = {1, 0, 0}, pb[3] = {0, 1, 0};
-    enc->n_mma = 3;
-    for (int i = 0; i < 3; ++i) { enc->mma_a[i] = pa[i]; enc->mma_b[i] = pb[i]; }
+    const int pa[3] = {1, 0, 0}, pb[3] = {0, 1, 0}, pc[3] = {1, 1, 0};
+    enc->n_mma = 3; enc->n_acc = 2;
+    for (int i = 0; i < 3; ++i) { enc->mma_a[i] = pa[i]; enc->mma_b[i] = pb[i]; enc->mma_acc[i] = pc[i]; }
   } else {
-    const int pa[6] = {2, 0, 1, 1, 0, 0}, pb[6] = {0, 2, 1, 0, 1, 0};
-    enc->n_mma = 6;
-    for (int i = 0; i < 6; ++i) { enc->mma_a[i] = pa[i]; enc->mma_b[i] = pb[i]; }
+    const int pa[6] = {2, 0, 1, 1, 0, 0}, pb[6] = {0, 2, 1, 0, 1, 0}, pc[6] = {1, 1, 1, 1, 1, 0};
+    enc->n_mma = 6; enc->n_acc = 2;
+    for (int i = 0; i < 6; ++i) { enc->mma_a[i] = pa[i]; enc->mma_b[i] = pb[i]; enc->mma_acc[i] = pc[i]; }
   }
   std::memcpy(enc->bifpn_w, bifpn_fusion_w_h, sizeof(enc->bifpn_w));
 
@@ -567,6 +597,10 @@ void dad3d_encoder_destroy(dad3d_encoder* enc) {
   }
   cudaFree(enc->d_stem_w);
   cudaFree(enc->d_stem_b);
+  for (auto& ev : enc->prof_events) {
+    cudaEventDestroy(ev.first);
+    cudaEventDestroy(ev.second);
+  }
   delete enc;
 }
 
@@ -676,6 +710,32 @@ int dad3d_encoder_forward(dad3d_encoder* enc, const float* images_d, int32_t B, 
     }
   }
   DAD3D_CUDA_OK(cudaGetLastError());
+  return DAD3D_OK;
+}
+
+// ---- live kernel timing for bench.py's roofline: events around every tile_gemm_kernel<EpiConv> launch
+int dad3d_encoder_set_profile(dad3d_encoder* enc, int32_t on) {
+  DAD3D_REQUIRE(enc, "null handle");
+  enc->profile = on != 0;
+  enc->prof_used = 0;
+  enc->prof_flops = 0.0;
+  return DAD3D_OK;
+}
+
+int dad3d_encoder_profile_read(dad3d_encoder* enc, double* gemm_ms, long long* gemm_launches, double* useful_flops) {
+  DAD3D_REQUIRE(enc && gemm_ms && gemm_launches && useful_flops, "null pointer");
+  double ms = 0.0;
+  for (size_t i = 0; i < enc->prof_used; ++i) {
+    DAD3D_CUDA_OK(cudaEventSynchronize(enc->prof_events[i].second));
+    float t = 0.f;
+    DAD3D_CUDA_OK(cudaEventElapsedTime(&t, enc->prof_events[i].first, enc->prof_events[i].second));
+    ms += t;
+  }
+  *gemm_ms = ms;
+  *gemm_launches = static_cast<long long>(enc->prof_used);
+  *useful_flops = enc->prof_flops;
+  enc->prof_used = 0;
+  enc->prof_flops = 0.0;
   return DAD3D_OK;
 }
 

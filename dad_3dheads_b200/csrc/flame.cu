@@ -584,12 +584,12 @@ int dad3d_flame_decode(dad3d_flame* h, const float* params_d, int32_t B, int32_t
       g.block_n = kBlendBlockN;
       g.fmt16 = 0;
       if (flags & DAD3D_BLEND_FAST) {
-        g.nA = 1; g.nB = 1; g.n_mma = 1; g.mma_a[0] = 0; g.mma_b[0] = 0;
+        g.nA = 1; g.nB = 1; g.n_mma = 1; g.mma_a[0] = 0; g.mma_b[0] = 0; g.mma_acc[0] = 0; g.n_acc = 1;
       } else {
-        g.nA = 2; g.nB = 2; g.n_mma = 3;
-        g.mma_a[0] = 1; g.mma_b[0] = 0;   // lo*hi and hi*lo first (small terms), hi*hi last
-        g.mma_a[1] = 0; g.mma_b[1] = 1;
-        g.mma_a[2] = 0; g.mma_b[2] = 0;
+        g.nA = 2; g.nB = 2; g.n_mma = 3; g.n_acc = 2;
+        g.mma_a[0] = 1; g.mma_b[0] = 0; g.mma_acc[0] = 1;   // lo*hi, hi*lo: small terms, own accumulator
+        g.mma_a[1] = 0; g.mma_b[1] = 1; g.mma_acc[1] = 1;
+        g.mma_a[2] = 0; g.mma_b[2] = 0; g.mma_acc[2] = 0;   // hi*hi
       }
       const int stage_bytes = gemm_stage_bytes(g);
       g.stages = (227 * 1024 - 2048) / stage_bytes;

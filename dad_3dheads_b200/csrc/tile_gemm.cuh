@@ -12,6 +12,11 @@
 // fp32 operand into "pieces" (x = p0 + p1 [+ p2], each piece 16-bit) stored as separate planes; the MMA list names which
 // (A piece, B piece) products are accumulated (1 product = plain 16-bit GEMM, 3 = hi*hi + hi*lo + lo*hi, 6 = three-way).
 //
+// Accumulator classes: the tensor core adds into its fp32 accumulator with truncation, so every MMA issued against a
+// LARGE accumulator costs up to one ulp of systematic (round-toward-zero) error.  With n_acc = 2 the dominant hi*hi
+// products go to accumulator 0 and all the small correction products to accumulator 1; the epilogue adds the two in
+// fp32 with round-to-nearest.  That cuts the number of truncating steps on the large accumulator by n_mma (6x / 3x).
+//
 // Roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one lane), warp 2 = TMEM allocator,
 // warps 4..7 = epilogue (thread t of the warpgroup owns accumulator row t = TMEM lane t).
 // Pipelines: smem ring (full/empty mbarriers) between TMA and MMA; two TMEM accumulators (tmem_full/tmem_empty)
@@ -42,6 +47,8 @@ struct GemmGeom {
   int nA, nB;                      // operand pieces
   int n_mma;                       // number of (a,b) piece products
   int mma_a[kMaxMma], mma_b[kMaxMma];
+  int n_acc;                       // 1 or 2 TMEM accumulators per tile (2 * n_acc * block_n <= 512 columns)
+  int mma_acc[kMaxMma];            // which accumulator each product goes to (see "accumulator classes" below)
   int stages;                      // smem ring depth
   unsigned fmt16;                  // 0 = fp16, 1 = bf16
 };
@@ -168,7 +175,8 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * g.block_n);
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * g.n_acc * g.block_n);
+        uint32_t started = 0;                        // bit a set once accumulator a has received its first MMA
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
@@ -177,10 +185,13 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
           for (int i = 0; i < g.n_mma; ++i) {
             const uint64_t adesc = ptx::make_kmajor_sw128_desc(sa + g.mma_a[i] * kTileABytes);
             const uint64_t bdesc = ptx::make_kmajor_sw128_desc(sb + g.mma_b[i] * g.block_n * kBlockK * 2);
+            const uint32_t a_id = static_cast<uint32_t>(g.mma_acc[i]);
+            const uint32_t d_acc = d_tmem + a_id * static_cast<uint32_t>(g.block_n);
 #pragma unroll
             for (int k = 0; k < kBlockK / 16; ++k) {
               // advancing 16 elements (32 B) along K inside the 128 B swizzle row = +2 in the (addr >> 4) field
-              ptx::umma_f16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | i | k) != 0 ? 1u : 0u);
+              ptx::umma_f16(d_acc, adesc + 2u * k, bdesc + 2u * k, idesc, (started >> a_id) & 1u);
+              started |= 1u << a_id;
             }
           }
           ptx::umma_commit(&empty_bar[stage]);   // smem slot reusable once these MMAs have read it
@@ -212,11 +223,20 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
       er.col0 = tc.n_tile * g.block_n;
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
       ptx::tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + static_cast<uint32_t>(acc * g.block_n);
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) +
+                             static_cast<uint32_t>(acc * g.n_acc * g.block_n);
       for (int c0 = 0; c0 < g.block_n; c0 += 32) {
         uint32_t v[32];
         ptx::tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(c0), v);
-        ptx::tmem_ld_wait();
+        if (g.n_acc == 2) {
+          uint32_t v2[32];
+          ptx::tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(g.block_n + c0), v2);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+        } else {
+          ptx::tmem_ld_wait();
+        }
         if (c0 + 32 >= g.block_n) {                // accumulator fully drained into registers: hand TMEM back early
           ptx::tc_fence_before();
           ptx::mbar_arrive(&tempty_bar[acc]);

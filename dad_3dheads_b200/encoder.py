@@ -155,6 +155,17 @@ class Dad3dEncoder:
     def eval(self):
         return self
 
+    # ---- live timing of the tile-engine launches (bench.py roofline)
+    def set_profile(self, on: bool = True) -> None:
+        _lib.check(self.lib.dad3d_encoder_set_profile(self._h, 1 if on else 0), "dad3d_encoder_set_profile")
+
+    def profile_read(self):
+        """-> (summed kernel ms, launches, algorithmic FLOPs) of the tile_gemm launches since the last read."""
+        ms, n, fl = C.c_double(), C.c_longlong(), C.c_double()
+        _lib.check(self.lib.dad3d_encoder_profile_read(self._h, C.byref(ms), C.byref(n), C.byref(fl)),
+                   "dad3d_encoder_profile_read")
+        return ms.value, n.value, fl.value
+
     # ---- test hooks (include/dad3d.h "test hooks")
     def set_debug(self, keep_all: bool = True) -> None:
         _lib.check(self.lib.dad3d_encoder_set_debug(self._h, 1 if keep_all else 0), "dad3d_encoder_set_debug")

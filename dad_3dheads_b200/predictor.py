@@ -1,0 +1,223 @@
+"""Host-side mirror of the reference's inference API (predictor.py:68-211) over libdad3d.so.
+
+``FaceMeshPredictor`` keeps the reference's constructor, ``dad_3dnet()``, ``__call__`` (HxWx3 uint8 RGB -> dict with
+"points", "projected_vertices", "3d_vertices", "3dmm_params"), the overridable ``preprocess / process / postprocess``
+stages and their helper names, so ``demo.py`` / ``demo_utils.py`` code written against the reference keeps working.
+What changes is where the arithmetic runs: ``self.model`` is the CUDA encoder (csrc/encoder.cu) instead of a TorchScript
+module, and ``self.head_mesh`` decodes on the GPU (csrc/flame.cu), once instead of twice per image.
+``predict_batch`` is the batched, device-resident entry point the reference does not have.
+"""
+from __future__ import annotations
+
+import logging
+import os
+from typing import Any, Dict, List, Optional, Tuple, Union
+
+import numpy as np
+import torch
+import yaml
+from torch import Tensor
+
+from . import _lib
+from .encoder import OUTPUT_2D_LANDMARKS, OUTPUT_3DMM_PARAMS, OUTPUT_LANDMARKS_HEATMAP, Dad3dEncoder
+from .flame import load_flame_static
+from .head_mesh import HeadMesh
+
+logger = logging.getLogger(__name__)
+_FILENAME = "dad_3dheads.trcd"
+_MEAN = (0.485, 0.456, 0.406)
+_STD = (0.229, 0.224, 0.225)
+
+DEFAULT_CONFIG = {                                   # == the reference's dad_3dnet.yaml
+    "model_path": ".dad_checkpoints/dad_3dheads.trcd",
+    "stride": 4,
+    "img_size": 256,
+    "constants": {"shape": 300, "expression": 100, "jaw": 3, "rotation": 6, "eyeballs": 0, "neck": 0,
+                  "translation": 3, "scale": 1},
+}
+
+
+def load_yaml(path: str) -> Dict[str, Any]:
+    with open(path) as fd:
+        return yaml.load(fd, yaml.FullLoader)
+
+
+def model_exists() -> bool:
+    return os.path.isfile(os.path.join(os.path.expanduser("~"), ".dad_checkpoints", _FILENAME))
+
+
+def py3round(number: float) -> int:
+    """albumentations.augmentations.geometric.py3round == Python-3 (banker's) rounding to int (predictor.py:12,121)."""
+    return int(round(number))
+
+
+def calculate_paddings(orig_h: int, orig_w: int) -> List[int]:
+    """model_training/model/utils.py:71-77 -> [pad_top, pad_bottom, pad_left, pad_right] to a centred square."""
+    side = max(orig_h, orig_w)
+    top = int((side - orig_h) / 2)
+    left = int((side - orig_w) / 2)
+    return [top, side - orig_h - top, left, side - orig_w - left]
+
+
+def letterbox_normalise(x: np.ndarray, img_size: int) -> np.ndarray:
+    """predictor.py:195-203 (albumentations 1.0.0 LongestMaxSize -> PadIfNeeded(constant 0, centred) -> Normalize),
+    restated with cv2/numpy: HxWx3 uint8 RGB -> img_size x img_size x 3 float32."""
+    import cv2
+    h, w = x.shape[:2]
+    scale = img_size / float(max(w, h))
+    if scale != 1.0:
+        nh, nw = py3round(h * scale), py3round(w * scale)
+        x = cv2.resize(x, dsize=(nw, nh), interpolation=cv2.INTER_LINEAR)
+    h, w = x.shape[:2]
+    top = int((img_size - h) / 2.0) if h < img_size else 0
+    bottom = (img_size - h - top) if h < img_size else 0
+    left = int((img_size - w) / 2.0) if w < img_size else 0
+    right = (img_size - w - left) if w < img_size else 0
+    if top or bottom or left or right:
+        x = cv2.copyMakeBorder(x, top, bottom, left, right, cv2.BORDER_CONSTANT, value=0)
+    mean = np.array(_MEAN, dtype=np.float32) * 255.0
+    denom = np.reciprocal(np.array(_STD, dtype=np.float32) * 255.0, dtype=np.float32)
+    out = x.astype(np.float32)
+    out -= mean
+    out *= denom
+    return out
+
+
+class FaceMeshPredictor:
+    def __init__(self, config: Dict[str, Any], cuda_id: int = 0, state_dict: Optional[Dict[str, Tensor]] = None,
+                 precision: str = "fp32"):
+        if not torch.cuda.is_available():
+            raise _lib.Dad3dError("FaceMeshPredictor needs a CUDA (sm_100a) device: there is no CPU path")
+        self.cuda_id = cuda_id
+        self.device = torch.device("cuda", cuda_id)
+        self.flame_constants = config["constants"]
+        if state_dict is None:
+            path = os.path.join(os.path.expanduser("~"), config["model_path"])
+            if not os.path.isfile(path):
+                raise FileNotFoundError(
+                    f"{path} not found. The reference downloads its TorchScript checkpoint on first use "
+                    f"(predictor.py:205-211); offline, pass state_dict= (e.g. encoder_weights.synthetic_state_dict).")
+            state_dict = torch.jit.load(path, map_location="cpu").state_dict()
+        self.model = Dad3dEncoder(state_dict, self.device, precision=precision).eval()
+        self.head_mesh = HeadMesh(self.flame_constants, cuda_id=cuda_id)
+        self._img_size = config["img_size"]
+        self._stride = config.get("stride", 2)
+        self._static = None
+
+    # ------------------------------------------------------------------ reference single-image API
+    def __call__(self, x: Any) -> Any:
+        cache: Dict[str, Any] = {}
+        x = self.preprocess(x, cache)
+        res = self.process(x, cache)
+        return self.postprocess(res, cache)
+
+    @staticmethod
+    def _array_to_batch(x: np.ndarray) -> Tensor:
+        return torch.from_numpy(np.expand_dims(np.transpose(x, (2, 0, 1)), 0))
+
+    def _transform(self, x: np.ndarray) -> np.ndarray:
+        return letterbox_normalise(x, self._img_size)
+
+    def preprocess(self, x: np.ndarray, cache: Dict[str, Any], *kw: Any) -> Tensor:
+        cache["input_shape"] = x.shape[:2]
+        x = self._array_to_batch(self._transform(x))
+        return x.to(self.device)
+
+    def process(self, x: Tensor, *kw: Any) -> Dict[str, Tensor]:
+        with torch.no_grad():
+            return self.model(x)
+
+    def _parse_output(self, x: Dict[str, Tensor]):
+        pred_3dmm = x[OUTPUT_3DMM_PARAMS].detach().cpu()
+        if OUTPUT_2D_LANDMARKS in x.keys():
+            pred_landmarks = x[OUTPUT_2D_LANDMARKS].detach().cpu().numpy() * 256.0
+        elif OUTPUT_LANDMARKS_HEATMAP in x.keys():
+            hm = torch.sigmoid(x[OUTPUT_LANDMARKS_HEATMAP]).detach()
+            B, C_, H, W = hm.shape                                    # model/utils.py:38-52 (divides by H for both axes)
+            idx = hm.view(B, C_, -1).argmax(-1).view(-1, 1)
+            kp = torch.cat((torch.div(idx, H, rounding_mode="trunc"), idx % H), dim=1).reshape(B, C_, 2)
+            pred_landmarks = float(self._stride) * kp.flip(-1)[0].cpu().numpy()
+        else:
+            return pred_3dmm
+        return pred_landmarks, pred_3dmm
+
+    def _get_paddings(self, cache: Dict[str, Any]) -> Tuple[List[int], float]:
+        h, w = cache["input_shape"]
+        scale = self._img_size / float(max(h, w))
+        new_h, new_w = tuple(py3round(dim * scale) for dim in (h, w))
+        return calculate_paddings(new_h, new_w), scale
+
+    def readjust_landmarks_to_the_input_image(self, landmarks: np.ndarray, paddings: List[int], scale: float):
+        landmarks = landmarks - np.array([[paddings[2], paddings[0]]])
+        return (landmarks / scale).astype(int)
+
+    @staticmethod
+    def find_3dmm_idx(key: str, consts: Dict[str, int]) -> int:
+        idx = 0
+        for k, v in consts.items():
+            if k == key:
+                break
+            idx += v
+        return idx
+
+    def readjust_3dmm_to_the_input_image(self, pred_3dmm: Tensor, paddings: List[int], scale: float) -> Tensor:
+        """predictor.py:154-176 -- in place on the 413-vector, so projections land in input-image pixels."""
+        si = self.find_3dmm_idx("scale", self.flame_constants)
+        ti = self.find_3dmm_idx("translation", self.flame_constants)
+        ns, nt = self.flame_constants["scale"], self.flame_constants["translation"]
+        new_scale = (pred_3dmm[:, si:si + ns] + 1.0) / scale - 1.0
+        pad = torch.tensor([[paddings[2], paddings[0], 0]], dtype=pred_3dmm.dtype, device=pred_3dmm.device)
+        new_t = (pred_3dmm[:, ti:ti + nt] + 1.0 - pad * 2 / self._img_size) / scale - 1.0
+        pred_3dmm[:, si:si + ns] = new_scale
+        pred_3dmm[:, ti:ti + nt] = new_t
+        return pred_3dmm
+
+    def _get_predictions(self, x, cache: Dict[str, Any]) -> Dict[str, Any]:
+        paddings, scale = self._get_paddings(cache)
+        if type(x) is tuple:
+            landmarks, pred_3dmm = x
+            landmarks = landmarks.clip(min=0, max=self._img_size)
+            landmarks = self.readjust_landmarks_to_the_input_image(landmarks, paddings, scale)
+            pred_3dmm = self.readjust_3dmm_to_the_input_image(pred_3dmm, paddings, scale)
+            # the reference decodes twice (predictor.py:136-137); one GPU pass yields both outputs
+            v3, proj = self.head_mesh.decode(pred_3dmm, to_2d=True)
+            ti = self.find_3dmm_idx("translation", self.flame_constants)
+            pred_3dmm[:, ti + 2] = 0.0                       # side effect of reprojected_vertices (head_mesh.py:41)
+            return {"points": landmarks, "projected_vertices": proj, "3d_vertices": v3[0].squeeze(),
+                    "3dmm_params": pred_3dmm}
+        return {"3dmm_params": self.readjust_3dmm_to_the_input_image(x, paddings, scale)}
+
+    def postprocess(self, x, cache: Dict[str, Any], *kw: Any) -> Dict[str, Any]:
+        predictions = self._get_predictions(self._parse_output(x), cache)
+        if "points" in predictions.keys():
+            predictions["points"] = np.reshape(predictions["points"], (-1, 2))
+        return predictions
+
+    @classmethod
+    def dad_3dnet(cls, state_dict: Optional[Dict[str, Tensor]] = None, precision: str = "fp32", cuda_id: int = 0):
+        here = os.path.dirname(os.path.abspath(__file__))
+        cfg_path = os.path.join(here, "dad_3dnet.yaml")
+        config = load_yaml(cfg_path) if os.path.isfile(cfg_path) else dict(DEFAULT_CONFIG)
+        return cls(config=config, cuda_id=cuda_id, state_dict=state_dict, precision=precision)
+
+    # ------------------------------------------------------------------ batched device-resident API (new)
+    def _landmark_index(self, subset: str) -> Tensor:
+        if self._static is None:
+            self._static = load_flame_static()
+        key = {"191": "keypoints_191", "445": "keypoints_445", "565": "keypoints_565"}[str(subset)]
+        return torch.from_numpy(self._static[key].astype(np.int64)).to(self.device)
+
+    def predict_batch(self, images: Tensor, landmark_subset: Optional[str] = "445", to_2d: bool = True,
+                      fast_decode: bool = False) -> Dict[str, Tensor]:
+        """images: [B,3,256,256] fp32 already letter-boxed + normalised (host or device).  All outputs stay on the GPU:
+        "3dmm_params" [B,413], "points" [B,68,2] (pixels of the 256x256 input), "3d_vertices" [B,5023,3],
+        "projected_vertices" [B,5023,2|3], "landmarks_<subset>" [B,L,2|3]."""
+        x = images.to(self.device, torch.float32, non_blocking=True)
+        params, lms, _ = self.model.forward_raw(x, want_heatmap=False)
+        v3, proj = self.head_mesh.decode(params, to_2d=to_2d, fast=fast_decode)
+        out = {"3dmm_params": params, "points": lms * float(self._img_size), "3d_vertices": v3,
+               "projected_vertices": proj}
+        if landmark_subset is not None:
+            dec = self.head_mesh.flame.decoder(self.device)
+            out[f"landmarks_{landmark_subset}"] = dec.gather(proj, self._landmark_index(landmark_subset))
+        return out

@@ -124,6 +124,14 @@ DAD3D_API int dad3d_encoder_forward(dad3d_encoder* enc, const float* images_d, i
                                     float* landmarks_d, float* heatmap_d, void* workspace_d, size_t workspace_bytes,
                                     dad3d_stream stream);
 
+/* Live timing of the dominant kernel (the tcgen05 tile engine) for bench.py's roofline: while on, every conv / linear
+ * launch is bracketed by CUDA events on the launching stream.  profile_read synchronises those events and returns their
+ * summed duration, the launch count and the ALGORITHMIC FLOPs (2 * true MACs, one product per MAC, no padding) of the
+ * recorded launches, then resets the counters. */
+DAD3D_API int dad3d_encoder_set_profile(dad3d_encoder* enc, int32_t on);
+DAD3D_API int dad3d_encoder_profile_read(dad3d_encoder* enc, double* gemm_ms, long long* gemm_launches,
+                                         double* useful_flops);
+
 /* test hooks: keep_all != 0 disables workspace reuse so that, after a forward, any activation can be read back by the
  * name of the layer that produced it ("stem", "s2u1c3", "b1_p4out", "cat", "fusion", "gap", "heat", "mlp2" ...) as fp32
  * NHWC with channels padded as stored; dims4 receives [N,H,W,C] (pass out_d = NULL to query the shape only). */

@@ -1,0 +1,111 @@
+"""-m gpu: the CUDA encoder (through the C ABI) against the CPU oracle's FlameRegression.forward, same seeded weights/inputs.
+
+Tolerances (norm-wise relative L2 vs the fp64 oracle; north_star contract: 1e-4 relative to the fp32 reference path):
+  "fp32"   (bf16 three-way split, 6 products, two-class accumulation)   < 3e-5   -- the parity mode
+  "bf16x2" (bf16 hi/lo, 3 products)                                      < 1e-4
+  "bf16"   (plain bf16 operands, throughput mode, BASELINE config 3)     < 2e-2   (NOT under the 1e-4 banner)
+"""
+import pytest
+import torch
+
+from dad_3dheads_b200.encoder_weights import synthetic_state_dict
+from oracle.encoder_oracle import (OUTPUT_2D_LANDMARKS, OUTPUT_3DMM_PARAMS, OUTPUT_LANDMARKS_HEATMAP,
+                                   flame_regression_forward)
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / b.norm()).item()
+
+
+@pytest.fixture(scope="module")
+def sd():
+    return synthetic_state_dict(0)
+
+
+@pytest.fixture(scope="module")
+def ref5(sd):
+    x = torch.randn(5, 3, 256, 256, generator=torch.Generator().manual_seed(42))
+    with torch.no_grad():
+        out = flame_regression_forward(x.double(), {k: v.double() for k, v in sd.items()})
+    return x, out
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 3e-5), ("bf16x2", 1e-4), ("bf16", 2e-2)])
+def test_encoder_matches_oracle(sd, ref5, cuda_device, precision, tol):
+    from dad_3dheads_b200.encoder import Dad3dEncoder
+    x, ref = ref5
+    enc = Dad3dEncoder(sd, cuda_device, precision=precision)
+    out = enc(x.to(cuda_device))
+    assert out[OUTPUT_3DMM_PARAMS].shape == (5, 413) and out[OUTPUT_2D_LANDMARKS].shape == (5, 68, 2)
+    assert out[OUTPUT_LANDMARKS_HEATMAP].shape == (5, 68, 64, 64)
+    errs = {k: _rel(out[k], ref[k]) for k in ref}
+    assert all(e < tol for e in errs.values()), errs
+
+
+def test_fp32_mode_elementwise_contract(sd, ref5, cuda_device):
+    """|err| <= 1e-4 * |ref| + 1e-4 on every one of the 413 params (values span +-3), vs the fp32 oracle itself."""
+    from dad_3dheads_b200.encoder import Dad3dEncoder
+    x, _ = ref5
+    with torch.no_grad():
+        ref32 = flame_regression_forward(x, sd)
+    out = Dad3dEncoder(sd, cuda_device, precision="fp32")(x.to(cuda_device))
+    p, r = out[OUTPUT_3DMM_PARAMS].cpu(), ref32[OUTPUT_3DMM_PARAMS]
+    assert ((p - r).abs() <= 1e-4 * r.abs() + 1e-4).all(), (p - r).abs().max()
+
+
+def test_per_layer_activations(sd, cuda_device):
+    """Every named activation against the CPU executor of the folded graph: localises a regression to one kernel."""
+    from dad_3dheads_b200.encoder import Dad3dEncoder, fold_state_dict
+    from tests.folded_ref import run_folded
+    x = torch.randn(2, 3, 256, 256, generator=torch.Generator().manual_seed(7))
+    layers, fw = fold_state_dict(sd)
+    with torch.no_grad():
+        ref = run_folded(x, layers, fw)
+    enc = Dad3dEncoder(sd, cuda_device, precision="fp32")
+    enc.set_debug(True)
+    enc.forward_raw(x.to(cuda_device))
+    bad = {}
+    for name in ["stem"] + [n for n, _, _ in layers if n != "stem"] + ["cat", "gap"]:
+        a = enc.read_activation(name)
+        r = ref[name]
+        if name in ("gap", "mlp1", "mlp2"):
+            got, want = a.reshape(a.shape[2], a.shape[3])[:, : r.shape[1]], r.flatten(1)
+        else:
+            got, want = a[..., : r.shape[1]].permute(0, 3, 1, 2), r
+            pad = a[..., r.shape[1]:]
+            if pad.numel() and name not in ("cat",):
+                assert pad.abs().max().item() == 0.0, f"{name}: padded channels must stay zero"
+        e = _rel(got, want)
+        if e > 3e-5:
+            bad[name] = e
+    assert not bad, bad
+
+
+def test_batch_independence_and_determinism(sd, cuda_device):
+    """Eval-mode network: an image's outputs must not depend on its batch (bit-exact), nor on the run."""
+    from dad_3dheads_b200.encoder import Dad3dEncoder
+    enc = Dad3dEncoder(sd, cuda_device, precision="fp32", want_heatmap=False)
+    x = torch.randn(7, 3, 256, 256, generator=torch.Generator().manual_seed(9)).to(cuda_device)
+    p7, l7, _ = enc.forward_raw(x)
+    p7b, _, _ = enc.forward_raw(x)
+    assert torch.equal(p7, p7b)
+    p1, l1, _ = enc.forward_raw(x[3:4])
+    assert torch.equal(p7[3:4], p1) and torch.equal(l7[3:4], l1)
+    p3, _, _ = enc.forward_raw(x[4:7])
+    assert torch.equal(p7[4:7], p3)
+
+
+def test_batch_64_matches_oracle_subset(sd, cuda_device):
+    """BASELINE configs[1] size: batch 64; oracle checked on a subset (CPU time), the rest by batch independence."""
+    from dad_3dheads_b200.encoder import Dad3dEncoder
+    x = torch.randn(64, 3, 256, 256, generator=torch.Generator().manual_seed(64))
+    enc = Dad3dEncoder(sd, cuda_device, precision="fp32", want_heatmap=False)
+    p, l, _ = enc.forward_raw(x.to(cuda_device))
+    sel = [0, 31, 63]
+    with torch.no_grad():
+        ref = flame_regression_forward(x[sel].double(), {k: v.double() for k, v in sd.items()})
+    assert _rel(p[sel], ref[OUTPUT_3DMM_PARAMS]) < 3e-5 and _rel(l[sel], ref[OUTPUT_2D_LANDMARKS]) < 3e-5
+    assert torch.isfinite(p).all()
