@@ -393,7 +393,7 @@ int make_plan(dad3d_encoder* enc, int B, void* ws, size_t ws_bytes, bool layout_
     g.n_acc = enc->n_acc;
     for (int i = 0; i < enc->n_mma; ++i) { g.mma_a[i] = enc->mma_a[i]; g.mma_b[i] = enc->mma_b[i]; g.mma_acc[i] = enc->mma_acc[i]; }
     g.fmt16 = 1;
-    g.stages = std::min(8, (227 * 1024 - 2048) / gemm_stage_bytes(g));
+    g.stages = gemm_max_stages(g);
     if (g.stages < 2) { set_error("layer " + w->name + ": pipeline does not fit shared memory"); return DAD3D_ERR_INVALID; }
     for (int p = 0; p < enc->P; ++p) {
       const uint64_t dims[4] = {static_cast<uint64_t>(ti.C), static_cast<uint64_t>(ti.W), static_cast<uint64_t>(ti.H),
@@ -423,6 +423,25 @@ int make_plan(dad3d_encoder* enc, int B, void* ws, size_t ws_bytes, bool layout_
       ep.out_plane = to.plane_elems();
       ep.out_planes = to.planes;
       ep.ld_out = to.C;
+      if (w->block_n != 64 && w->block_n != 128) {
+        set_error("layer " + w->name + ": piece outputs need block_n 64 or 128");
+        return DAD3D_ERR_INVALID;
+      }
+      // per-warp store box: 32 consecutive tile rows = (bw x bh x bn) output pixels, block_n/2 channels
+      const int nc = w->block_n / 2;
+      const int bw = std::min(g.tw, 32);
+      const int bh = std::min(g.th, 32 / bw);
+      const int bn = 32 / (bw * bh);
+      for (int p = 0; p < to.planes; ++p) {
+        const uint64_t dims[4] = {static_cast<uint64_t>(to.C), static_cast<uint64_t>(to.W), static_cast<uint64_t>(to.H),
+                                  static_cast<uint64_t>(to.N)};
+        const uint64_t strides[3] = {static_cast<uint64_t>(to.C) * 2, static_cast<uint64_t>(to.W) * to.C * 2,
+                                     static_cast<uint64_t>(to.H) * to.W * to.C * 2};
+        const uint32_t box[4] = {static_cast<uint32_t>(nc), static_cast<uint32_t>(bw), static_cast<uint32_t>(bh),
+                                 static_cast<uint32_t>(bn)};
+        uint16_t* basep = reinterpret_cast<uint16_t*>(to.ptr) + static_cast<size_t>(p) * to.plane_elems();
+        if (!make_tmap_16bit(&s.maps.c[p], basep, 4, dims, strides, box, nullptr, nc * 2)) return DAD3D_ERR_CUDA;
+      }
     }
     if (s.out_f32 >= 0) {
       const TensorInfo& to = plan->tensors[s.out_f32];
@@ -446,7 +465,7 @@ double conv_useful_flops(const Step& s) {
 int launch_conv(dad3d_encoder* enc, const Step& s, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    DAD3D_CUDA_OK(cudaFuncSetAttribute(tile_gemm_kernel<EpiConv>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DAD3D_CUDA_OK(cudaFuncSetAttribute(tile_gemm_kernel<EpiConv>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemLimit));
     configured = true;
   }
   const GemmGeom& g = s.geom;

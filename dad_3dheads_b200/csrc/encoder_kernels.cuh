@@ -86,38 +86,98 @@ struct EpiConv {
     float* out_f32;           // optional fp32 copy [pix][ld_f32]
     int ld_f32;
   };
-  static __device__ __forceinline__ void apply(const Params& ep, const EpiRow& er, int c0, const uint32_t (&v)[32]) {
-    if (!er.valid) return;
-    const int col = er.col0 + c0;
+  // fp32-only outputs (heat-map, MLP logits): direct vector stores of this thread's row
+  static __device__ __forceinline__ void run_f32(const Params& ep, const EpiCtx& c) {
+    int cb, ce;
+    epi_chunk_range(*c.g, c.grp, &cb, &ce);
+    if (cb >= ce) epi_release_tmem(c);
+    for (int ch = cb; ch < ce; ++ch) {
+      float x[32];
+      epi_load32(c, ch * 32, x);
+      if (ch == ce - 1) epi_release_tmem(c);
+      if (!c.valid) continue;
+      const int col = c.col0 + ch * 32;
+      float4* d = reinterpret_cast<float4*>(ep.out_f32 + c.pix * ep.ld_f32 + col);
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {            // 4 groups of 8 channels
-      float x[8];
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + col + 8 * g));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + col + 8 * g + 4));
-      x[0] = __uint_as_float(v[8 * g + 0]) + b0.x;
-      x[1] = __uint_as_float(v[8 * g + 1]) + b0.y;
-      x[2] = __uint_as_float(v[8 * g + 2]) + b0.z;
-      x[3] = __uint_as_float(v[8 * g + 3]) + b0.w;
-      x[4] = __uint_as_float(v[8 * g + 4]) + b1.x;
-      x[5] = __uint_as_float(v[8 * g + 5]) + b1.y;
-      x[6] = __uint_as_float(v[8 * g + 6]) + b1.z;
-      x[7] = __uint_as_float(v[8 * g + 7]) + b1.w;
-      if (ep.res_mode != 0) {
+      for (int j = 0; j < 8; ++j) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col) + j);
+        float4 o = make_float4(x[4 * j] + b.x, x[4 * j + 1] + b.y, x[4 * j + 2] + b.z, x[4 * j + 3] + b.w);
+        if (ep.relu) {
+          o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+        }
+        d[j] = o;
+      }
+    }
+  }
+
+  // piece outputs: NC = block_n / 2 columns per warp (32 or 64).  The warp's 32 rows x NC channels are staged in its
+  // private shared-memory tile in the TMA swizzle pattern and written with ONE bulk tensor store per piece plane
+  // (out-of-range rows of partial tiles are clipped by the tensor map).
+  template <int NC>
+  static __device__ __forceinline__ void run_pieces(const Params& ep, const EpiCtx& c) {
+    float x[NC];
+    const int colw = c.grp * NC;                      // first column of this warp inside the tile
+#pragma unroll
+    for (int ch = 0; ch < NC / 32; ++ch) {
+      float t[32];
+      epi_load32(c, colw + ch * 32, t);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[ch * 32 + j] = t[j];
+    }
+    epi_release_tmem(c);
+    const int col = c.col0 + colw;
+#pragma unroll
+    for (int j = 0; j < NC / 4; ++j) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col) + j);
+      x[4 * j] += b.x; x[4 * j + 1] += b.y; x[4 * j + 2] += b.z; x[4 * j + 3] += b.w;
+    }
+    if (ep.res_mode != 0 && c.valid) {
+#pragma unroll
+      for (int gq = 0; gq < NC / 8; ++gq) {
         float r[8];
-        act_load8(ep.res, er.pix * ep.res.C + col + 8 * g, r);
+        act_load8(ep.res, c.pix * ep.res.C + col + 8 * gq, r);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = (ep.res_mode == 1) ? (x[j] + r[j]) : (x[j] * r[j]);
+        for (int j = 0; j < 8; ++j) x[8 * gq + j] = (ep.res_mode == 1) ? (x[8 * gq + j] + r[j]) : (x[8 * gq + j] * r[j]);
       }
-      if (ep.relu) {
+    }
+    if (ep.relu) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = fmaxf(x[j], 0.f);
+      for (int j = 0; j < NC; ++j) x[j] = fmaxf(x[j], 0.f);
+    }
+    constexpr int kRowBytes = NC * 2;                 // 64 (SWIZZLE_64B) or 128 (SWIZZLE_128B)
+    const int swz = (NC == 64) ? (c.lane & 7) : ((c.lane >> 1) & 3);
+    uint8_t* rowp = c.stage + c.lane * kRowBytes;
+    for (int p = 0; p < ep.out_planes; ++p) {
+      if (c.lane == 0) ptx::bulk_wait_read0();        // previous store has finished reading the staging tile
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < NC / 8; ++q) {              // 16-byte chunks of this row
+        uint32_t w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint16_t lo = bf16_bits(x[8 * q + 2 * j]), hi = bf16_bits(x[8 * q + 2 * j + 1]);
+          x[8 * q + 2 * j] -= bf16_to_f32(lo);
+          x[8 * q + 2 * j + 1] -= bf16_to_f32(hi);
+          w[j] = static_cast<uint32_t>(lo) | (static_cast<uint32_t>(hi) << 16);
+        }
+        *reinterpret_cast<uint4*>(rowp + ((q ^ swz) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
       }
-      if (ep.out) act_store8(ep.out, ep.out_plane, ep.out_planes, er.pix * ep.ld_out + col + 8 * g, x);
-      if (ep.out_f32) {
-        float4* d = reinterpret_cast<float4*>(ep.out_f32 + er.pix * ep.ld_f32 + col + 8 * g);
-        d[0] = make_float4(x[0], x[1], x[2], x[3]);
-        d[1] = make_float4(x[4], x[5], x[6], x[7]);
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (c.lane == 0) {
+        ptx::tma_store_4d(&c.maps->c[p], c.stage, col, c.bw0, c.bh0, c.bn0);
+        ptx::bulk_commit();
       }
+    }
+  }
+
+  static __device__ __forceinline__ void run(const Params& ep, const EpiCtx& c) {
+    if (ep.out == nullptr) {
+      run_f32(ep, c);
+    } else if (c.g->block_n == 128) {
+      run_pieces<64>(ep, c);
+    } else {
+      run_pieces<32>(ep, c);
     }
   }
 };

@@ -195,20 +195,28 @@ struct EpiBlend {
     const float* tmpl;   // [npad] template vertices (fp32, exact)
     float inv_scale;     // undo the power-of-two scaling of the fp16 basis
   };
-  static __device__ __forceinline__ void apply(const Params& ep, const EpiRow& er, int c0, const uint32_t (&v)[32]) {
-    if (!er.valid) return;
-    const int col = er.col0 + c0;
-    float4* dst = reinterpret_cast<float4*>(ep.out + static_cast<size_t>(er.pix) * ep.ld + col);
-    const float4* t4 = reinterpret_cast<const float4*>(ep.tmpl + col);
+  static __device__ __forceinline__ void run(const Params& ep, const EpiCtx& c) {
+    int cb, ce;
+    epi_chunk_range(*c.g, c.grp, &cb, &ce);
+    if (cb >= ce) epi_release_tmem(c);
+    for (int ch = cb; ch < ce; ++ch) {
+      float x[32];
+      epi_load32(c, ch * 32, x);
+      if (ch == ce - 1) epi_release_tmem(c);
+      if (!c.valid) continue;
+      const int col = c.col0 + ch * 32;
+      float4* dst = reinterpret_cast<float4*>(ep.out + static_cast<size_t>(c.pix) * ep.ld + col);
+      const float4* t4 = reinterpret_cast<const float4*>(ep.tmpl + col);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float4 t = __ldg(&t4[j]);
-      float4 o;
-      o.x = fmaf(__uint_as_float(v[4 * j + 0]), ep.inv_scale, t.x);
-      o.y = fmaf(__uint_as_float(v[4 * j + 1]), ep.inv_scale, t.y);
-      o.z = fmaf(__uint_as_float(v[4 * j + 2]), ep.inv_scale, t.z);
-      o.w = fmaf(__uint_as_float(v[4 * j + 3]), ep.inv_scale, t.w);
-      dst[j] = o;
+      for (int j = 0; j < 8; ++j) {
+        const float4 t = __ldg(&t4[j]);
+        float4 o;
+        o.x = fmaf(x[4 * j + 0], ep.inv_scale, t.x);
+        o.y = fmaf(x[4 * j + 1], ep.inv_scale, t.y);
+        o.z = fmaf(x[4 * j + 2], ep.inv_scale, t.z);
+        o.w = fmaf(x[4 * j + 3], ep.inv_scale, t.w);
+        dst[j] = o;
+      }
     }
   }
 };
@@ -354,8 +362,8 @@ int launch_tile_gemm(const GemmMaps& maps, const GemmGeom& g, const typename Epi
   static int configured_smem = 0;
   const int smem = gemm_smem_bytes(g);
   if (smem > configured_smem) {
-    DAD3D_CUDA_OK(cudaFuncSetAttribute(tile_gemm_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured_smem = 227 * 1024;
+    DAD3D_CUDA_OK(cudaFuncSetAttribute(tile_gemm_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemLimit));
+    configured_smem = kGemmSmemLimit;
   }
   const int total = g.tiles_w * g.tiles_h * g.tiles_n * g.n_tiles;
   const int grid = total < num_sms ? total : num_sms;
@@ -591,9 +599,7 @@ int dad3d_flame_decode(dad3d_flame* h, const float* params_d, int32_t B, int32_t
         g.mma_a[1] = 0; g.mma_b[1] = 1; g.mma_acc[1] = 1;
         g.mma_a[2] = 0; g.mma_b[2] = 0; g.mma_acc[2] = 0;   // hi*hi
       }
-      const int stage_bytes = gemm_stage_bytes(g);
-      g.stages = (227 * 1024 - 2048) / stage_bytes;
-      if (g.stages > 8) g.stages = 8;
+      g.stages = gemm_max_stages(g);
       EpiBlend::Params ep{vposed, h->npad, h->d_tmpl, inv_scale};
       int rc = launch_tile_gemm<EpiBlend>(maps, g, ep, h->num_sms, stream);
       if (rc != DAD3D_OK) return rc;

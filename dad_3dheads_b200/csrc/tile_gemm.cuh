@@ -17,10 +17,12 @@
 // products go to accumulator 0 and all the small correction products to accumulator 1; the epilogue adds the two in
 // fp32 with round-to-nearest.  That cuts the number of truncating steps on the large accumulator by n_mma (6x / 3x).
 //
-// Roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one lane), warp 2 = TMEM allocator,
-// warps 4..7 = epilogue (thread t of the warpgroup owns accumulator row t = TMEM lane t).
-// Pipelines: smem ring (full/empty mbarriers) between TMA and MMA; two TMEM accumulators (tmem_full/tmem_empty)
-// between MMA and epilogue, so the epilogue of tile i overlaps the main loop of tile i+1.
+// Roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one lane), warp 2 = TMEM allocator, warps 4..11 =
+// epilogue: warp w owns TMEM lanes 32*(w%4).. (accumulator rows) and column group (w-4)/4 (half of the tile's columns),
+// i.e. two epilogue warps per SM sub-partition so their dependent-issue stalls overlap.
+// Pipelines: smem ring (full/empty mbarriers) between TMA and MMA; two TMEM accumulator buffers (tmem_full/tmem_empty)
+// between MMA and epilogue, so the epilogue of tile i overlaps the main loop of tile i+1.  Each epilogue warp owns a
+// 4 KiB shared-memory staging tile from which it issues TMA stores of its 32 rows x (32|64) channels.
 #pragma once
 #include "ptx.cuh"
 
@@ -31,8 +33,11 @@ constexpr int kBlockK = 64;                       // 64 x 16-bit = 128 B = one s
 constexpr int kTileABytes = kBlockM * kBlockK * 2;   // 16 KiB per A piece per stage
 constexpr int kMaxPieces = 3;
 constexpr int kMaxMma = 6;
-constexpr int kGemmThreads = 256;
+constexpr int kEpiWarps = 8;
+constexpr int kGemmThreads = 128 + kEpiWarps * 32;   // 384
 constexpr int kTmemCols = 512;
+constexpr int kStageOutBytes = 4096;              // per epilogue warp: 32 rows x 128 B
+constexpr int kGemmSmemLimit = 227 * 1024;
 
 struct GemmGeom {
   // output tile = tn images x th rows x tw columns of output pixels (tw*th*tn == 128); plain GEMM: tw=128, th=tn=1
@@ -48,7 +53,7 @@ struct GemmGeom {
   int n_mma;                       // number of (a,b) piece products
   int mma_a[kMaxMma], mma_b[kMaxMma];
   int n_acc;                       // 1 or 2 TMEM accumulators per tile (2 * n_acc * block_n <= 512 columns)
-  int mma_acc[kMaxMma];            // which accumulator each product goes to (see "accumulator classes" below)
+  int mma_acc[kMaxMma];            // which accumulator each product goes to (see "accumulator classes" above)
   int stages;                      // smem ring depth
   unsigned fmt16;                  // 0 = fp16, 1 = bf16
 };
@@ -56,14 +61,18 @@ struct GemmGeom {
 struct GemmMaps {
   CUtensorMap a[kMaxPieces];       // rank-4 (C, W, H, N), box (64, tw*stride, th*stride, tn), swizzle 128B
   CUtensorMap b[kMaxPieces];       // rank-2 (Ktot, Cout_pad), box (64, block_n), swizzle 128B
+  CUtensorMap c[kMaxPieces];       // output planes, rank-4 (C, Wo, Ho, N), box (block_n/2, 32-pixel sub-box), for TMA stores
 };
 
 __host__ __device__ inline int gemm_stage_bytes(const GemmGeom& g) {
   return g.nA * kTileABytes + g.nB * g.block_n * kBlockK * 2;
 }
-__host__ inline int gemm_smem_bytes(const GemmGeom& g) {
-  return g.stages * gemm_stage_bytes(g) + 1024 /*align slack*/ + 256 /*barriers*/;
+__host__ inline int gemm_fixed_smem_bytes() { return kEpiWarps * kStageOutBytes + 1024 /*align slack*/ + 256 /*barriers*/; }
+__host__ inline int gemm_max_stages(const GemmGeom& g) {
+  int s = (kGemmSmemLimit - gemm_fixed_smem_bytes()) / gemm_stage_bytes(g);
+  return s > 8 ? 8 : s;
 }
+__host__ inline int gemm_smem_bytes(const GemmGeom& g) { return g.stages * gemm_stage_bytes(g) + gemm_fixed_smem_bytes(); }
 
 struct TileCoord {
   int m_tile, n_tile;
@@ -83,14 +92,53 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmGeom& g, int t) {
   return c;
 }
 
-// What an epilogue sees for its accumulator row.
-struct EpiRow {
-  int row;          // 0..127 inside the tile
-  int n, h, w;      // output pixel of this row (plain GEMM: w = global row index)
-  bool valid;       // inside the output extents
-  long long pix;    // linear output pixel index ((n*Ho + h)*Wo + w)
-  int col0;         // first output column (channel) of the tile
+// Everything an epilogue warp needs for one tile.
+struct EpiCtx {
+  const GemmGeom* g;
+  const GemmMaps* maps;
+  TileCoord tc;
+  int wq;            // TMEM lane quarter of this warp (0..3): accumulator rows 32*wq .. 32*wq+31
+  int grp;           // column group (0/1)
+  int lane;
+  uint32_t t_acc;    // TMEM address of (lane quarter, accumulator buffer of this tile, accumulator class 0, column 0)
+  uint8_t* stage;    // warp-private 4 KiB staging tile (1024-byte aligned)
+  uint64_t* tempty;  // arrive here (every epilogue thread, once) when the accumulator has been drained into registers
+  // this thread's accumulator row
+  int n, h, w;
+  bool valid;
+  long long pix;     // (n*Ho + h)*Wo + w
+  int col0;          // first output column of the tile
+  // the warp's 32-row sub-box origin inside the output tensor
+  int bw0, bh0, bn0;
 };
+
+// columns [c0, c0+32) of this thread's row, both accumulator classes summed (fp32, round-to-nearest)
+__device__ __forceinline__ void epi_load32(const EpiCtx& c, int c0, float (&x)[32]) {
+  uint32_t v[32];
+  ptx::tmem_ld_32x32b_x32(c.t_acc + static_cast<uint32_t>(c0), v);
+  if (c.g->n_acc == 2) {
+    uint32_t v2[32];
+    ptx::tmem_ld_32x32b_x32(c.t_acc + static_cast<uint32_t>(c.g->block_n + c0), v2);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) + __uint_as_float(v2[j]);
+  } else {
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+  }
+}
+__device__ __forceinline__ void epi_release_tmem(const EpiCtx& c) {
+  ptx::tc_fence_before();
+  ptx::mbar_arrive(c.tempty);
+}
+// 32-column chunks [cb, ce) of the tile that column group grp handles
+__device__ __forceinline__ void epi_chunk_range(const GemmGeom& g, int grp, int* cb, int* ce) {
+  const int nch = g.block_n / 32;
+  const int per = (nch + 1) / 2;
+  *cb = grp * per;
+  *ce = min(nch, *cb + per);
+}
 
 template <class Epi>
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -99,7 +147,8 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
   // 1024-byte alignment is required by the 128B swizzle atoms (TMA writes and UMMA reads must agree on the pattern).
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stage_bytes = gemm_stage_bytes(g);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + g.stages * stage_bytes);
+  uint8_t* out_stage = smem + g.stages * stage_bytes;                           // [kEpiWarps][4 KiB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + kEpiWarps * kStageOutBytes);
   uint64_t* full_bar = bars;                     // [stages]
   uint64_t* empty_bar = bars + g.stages;         // [stages]
   uint64_t* tfull_bar = bars + 2 * g.stages;     // [2]
@@ -122,7 +171,7 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(&tfull_bar[b], 1);
-      ptx::mbar_init(&tempty_bar[b], 128);
+      ptx::mbar_init(&tempty_bar[b], kEpiWarps * 32);
     }
     ptx::fence_mbar_init();
   }
@@ -203,49 +252,42 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
       }
     }
   } else if (warp >= 4) {
-    // ===================================================== epilogue warpgroup
-    const int wq = warp & 3;                       // TMEM lane quarter this warp may touch
-    const int row = wq * 32 + lane;
+    // ===================================================== epilogue warps
+    EpiCtx c;
+    c.g = &g;
+    c.maps = &maps;
+    c.wq = warp & 3;
+    c.grp = (warp - 4) >> 2;
+    c.lane = lane;
+    c.stage = out_stage + (warp - 4) * kStageOutBytes;
+    const int row = c.wq * 32 + lane;
+    const int iw = row % g.tw;
+    const int ih = (row / g.tw) % g.th;
+    const int in = row / (g.tw * g.th);
+    const int row0 = c.wq * 32;
+    const int biw = row0 % g.tw, bih = (row0 / g.tw) % g.th, bin = row0 / (g.tw * g.th);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const TileCoord tc = decode_tile(g, t);
-      EpiRow er;
-      er.row = row;
-      const int iw = row % g.tw;
-      const int ih = (row / g.tw) % g.th;
-      const int in = row / (g.tw * g.th);
-      er.n = tc.n0 + in;
-      er.h = tc.h0 + ih;
-      er.w = tc.w0 + iw;
-      er.valid = (er.n < g.Nimg) && (er.h < g.Ho) && (er.w < g.Wo);
-      er.pix = (static_cast<long long>(er.n) * g.Ho + er.h) * g.Wo + er.w;
-      er.col0 = tc.n_tile * g.block_n;
+      c.tc = decode_tile(g, t);
+      c.n = c.tc.n0 + in;
+      c.h = c.tc.h0 + ih;
+      c.w = c.tc.w0 + iw;
+      c.valid = (c.n < g.Nimg) && (c.h < g.Ho) && (c.w < g.Wo);
+      c.pix = (static_cast<long long>(c.n) * g.Ho + c.h) * g.Wo + c.w;
+      c.col0 = c.tc.n_tile * g.block_n;
+      c.bw0 = c.tc.w0 + biw;
+      c.bh0 = c.tc.h0 + bih;
+      c.bn0 = c.tc.n0 + bin;
+      c.tempty = &tempty_bar[acc];
+      c.t_acc = tmem_base + (static_cast<uint32_t>(c.wq * 32) << 16) + static_cast<uint32_t>(acc * g.n_acc * g.block_n);
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
       ptx::tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) +
-                             static_cast<uint32_t>(acc * g.n_acc * g.block_n);
-      for (int c0 = 0; c0 < g.block_n; c0 += 32) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(c0), v);
-        if (g.n_acc == 2) {
-          uint32_t v2[32];
-          ptx::tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(g.block_n + c0), v2);
-          ptx::tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
-        } else {
-          ptx::tmem_ld_wait();
-        }
-        if (c0 + 32 >= g.block_n) {                // accumulator fully drained into registers: hand TMEM back early
-          ptx::tc_fence_before();
-          ptx::mbar_arrive(&tempty_bar[acc]);
-        }
-        Epi::apply(ep, er, c0, v);
-      }
+      Epi::run(ep, c);                             // must call epi_release_tmem(c) exactly once per thread
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
+    if (lane == 0) ptx::bulk_wait_read0();         // staging tile must outlive the last TMA store's read
   }
 
   ptx::tc_fence_before();

@@ -30,10 +30,11 @@ inline PFN_encodeTiled get_encode_fn() {
 }
 
 // 16-bit element tensor, rank r (<= 4).  dims[0] is the innermost (contiguous) extent; strides_bytes[i] is the byte
-// stride of dim i+1.  box[] is in tensor elements BEFORE the traversal stride (elem_strides), swizzle is always 128B
-// (so box[0] * 2 bytes must be 128).  Out-of-bounds elements read as zero.
+// stride of dim i+1.  box[] is in tensor elements BEFORE the traversal stride (elem_strides); swizzle_bytes (128 / 64 / 0)
+// must equal box[0] * 2 bytes for the swizzled modes.  Out-of-bounds elements read as zero / are not written.
 inline bool make_tmap_16bit(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                            const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides) {
+                            const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides,
+                            int swizzle_bytes = 128) {
   PFN_encodeTiled fn = get_encode_fn();
   if (!fn) return false;
   cuuint64_t gdim[5];
@@ -47,7 +48,9 @@ inline bool make_tmap_16bit(CUtensorMap* out, const void* base, int rank, const 
   }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim,
-                  gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                       : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE),
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)) + " (rank " +
