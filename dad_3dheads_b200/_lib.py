@@ -11,6 +11,7 @@ DAD3D_ZERO_ROT = 1
 DAD3D_ZERO_JAW = 2
 DAD3D_BLEND_FAST = 4
 DAD3D_BLEND_SIMT = 8
+DAD3D_DECODE_UNFUSED = 16
 
 
 class Dad3dError(RuntimeError):

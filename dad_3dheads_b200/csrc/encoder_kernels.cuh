@@ -74,6 +74,7 @@ __device__ __forceinline__ void act_store8(uint16_t* base, long long plane, int 
 
 // ------------------------------------------------------------------------------------------------ conv epilogue
 struct EpiConv {
+  static constexpr int kExtraSmemBytes = 0;
   struct Params {
     const float* bias;        // [Cout_pad] folded BN shift / conv bias
     int relu;
@@ -93,7 +94,7 @@ struct EpiConv {
     if (cb >= ce) epi_release_tmem(c);
     for (int ch = cb; ch < ce; ++ch) {
       float x[32];
-      epi_load32(c, ch * 32, x);
+      epi_load32<0>(c, ch * 32, x);
       if (ch == ce - 1) epi_release_tmem(c);
       if (!c.valid) continue;
       const int col = c.col0 + ch * 32;
@@ -117,13 +118,8 @@ struct EpiConv {
   static __device__ __forceinline__ void run_pieces(const Params& ep, const EpiCtx& c) {
     float x[NC];
     const int colw = c.grp * NC;                      // first column of this warp inside the tile
-#pragma unroll
-    for (int ch = 0; ch < NC / 32; ++ch) {
-      float t[32];
-      epi_load32(c, colw + ch * 32, t);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) x[ch * 32 + j] = t[j];
-    }
+    epi_load32<0>(c, colw, x);
+    if constexpr (NC == 64) epi_load32<32>(c, colw + 32, x);
     epi_release_tmem(c);
     const int col = c.col0 + colw;
 #pragma unroll
@@ -131,22 +127,74 @@ struct EpiConv {
       const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col) + j);
       x[4 * j] += b.x; x[4 * j + 1] += b.y; x[4 * j + 2] += b.z; x[4 * j + 3] += b.w;
     }
-    if (ep.res_mode != 0 && c.valid) {
+    constexpr int kRowBytes = NC * 2;                 // 64 (SWIZZLE_64B) or 128 (SWIZZLE_128B)
+    const int swz = (NC == 64) ? (c.lane & 7) : ((c.lane >> 1) & 3);
+    uint8_t* rowp = c.stage + c.lane * kRowBytes;
+    if (ep.res_mode != 0) {
+      // Residual / gate operand: the warp's 32 rows x NC channels per piece plane.  Loaded COOPERATIVELY (each warp
+      // instruction covers whole 64/128-byte row segments -> 4-8 memory wavefronts instead of 32 for per-thread rows),
+      // transposed through the staging tile (same swizzle as the output path), then every lane reads back its own row.
+      constexpr int kSegs = NC / 8;                   // 16-byte segments per row
+      if (c.lane == 0) ptx::bulk_wait_read0();        // the previous tile's last store may still be reading the tile
+      __syncwarp();
+      auto stage_plane = [&](int p) {
 #pragma unroll
-      for (int gq = 0; gq < NC / 8; ++gq) {
-        float r[8];
-        act_load8(ep.res, c.pix * ep.res.C + col + 8 * gq, r);
+        for (int it = 0; it < kSegs; ++it) {
+          const int idx = it * 32 + c.lane;
+          const int row = idx / kSegs, seg = idx % kSegs;
+          const long long spix = __shfl_sync(0xffffffffu, c.pix, row);
+          const int svalid = __shfl_sync(0xffffffffu, c.valid ? 1 : 0, row);
+          uint4 q = make_uint4(0, 0, 0, 0);
+          if (svalid) q = __ldg(reinterpret_cast<const uint4*>(ep.res.base + p * ep.res.plane + spix * ep.res.C + col + seg * 8));
+          const int rswz = (NC == 64) ? (row & 7) : ((row >> 1) & 3);
+          *reinterpret_cast<uint4*>(c.stage + row * kRowBytes + ((seg ^ rswz) << 4)) = q;
+        }
+        __syncwarp();
+      };
+      if (ep.res_mode == 1) {                         // ResUnit: x += identity (pieces added smallest first)
+        for (int p = ep.res.planes - 1; p >= 0; --p) {
+          stage_plane(p);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) x[8 * gq + j] = (ep.res_mode == 1) ? (x[8 * gq + j] + r[j]) : (x[8 * gq + j] * r[j]);
+          for (int q8 = 0; q8 < kSegs; ++q8) {
+            const uint4 q = *reinterpret_cast<const uint4*>(rowp + ((q8 ^ swz) << 4));
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              x[8 * q8 + 2 * j] += __uint_as_float(w[j] << 16);
+              x[8 * q8 + 2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+            }
+          }
+          __syncwarp();
+        }
+      } else {                                        // FusionLayer gate: x *= (p0 + p1 + p2), 32 columns at a time
+#pragma unroll
+        for (int half = 0; half < NC / 32; ++half) {
+          float rs[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) rs[j] = 0.f;
+          for (int p = ep.res.planes - 1; p >= 0; --p) {
+            stage_plane(p);
+#pragma unroll
+            for (int q8 = 0; q8 < 4; ++q8) {
+              const uint4 q = *reinterpret_cast<const uint4*>(rowp + (((half * 4 + q8) ^ swz) << 4));
+              const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                rs[8 * q8 + 2 * j] += __uint_as_float(w[j] << 16);
+                rs[8 * q8 + 2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+              }
+            }
+            __syncwarp();
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[half * 32 + j] *= rs[j];
+        }
       }
     }
     if (ep.relu) {
 #pragma unroll
       for (int j = 0; j < NC; ++j) x[j] = fmaxf(x[j], 0.f);
     }
-    constexpr int kRowBytes = NC * 2;                 // 64 (SWIZZLE_64B) or 128 (SWIZZLE_128B)
-    const int swz = (NC == 64) ? (c.lane & 7) : ((c.lane >> 1) & 3);
-    uint8_t* rowp = c.stage + c.lane * kRowBytes;
     for (int p = 0; p < ep.out_planes; ++p) {
       if (c.lane == 0) ptx::bulk_wait_read0();        // previous store has finished reading the staging tile
       __syncwarp();
@@ -212,22 +260,22 @@ stem_conv_kernel(const float* __restrict__ img, const float* __restrict__ w /*[1
   }
   __syncthreads();
   const int ty = t / kStemTile, tx = t % kStemTile;
-  float acc[64];
+  // 64 output channels as 32 packed pairs: fma.rn.f32x2 (sm_100) issues two fp32 FMAs per instruction
+  float2 acc[32];
 #pragma unroll
-  for (int o = 0; o < 64; ++o) acc[o] = 0.f;
+  for (int o = 0; o < 32; ++o) acc[o] = make_float2(0.f, 0.f);
   for (int c = 0; c < 3; ++c)
     for (int ky = 0; ky < 7; ++ky)
 #pragma unroll
       for (int kx = 0; kx < 7; ++kx) {
-        const float xv = s_in[c][ty * 2 + ky][tx * 2 + kx];
+        const float xs = s_in[c][ty * 2 + ky][tx * 2 + kx];
+        const float2 xv = make_float2(xs, xs);
         const float4* wr = reinterpret_cast<const float4*>(&s_w[((c * 7 + ky) * 7 + kx) * 64]);
 #pragma unroll
         for (int o = 0; o < 16; ++o) {
           const float4 q = wr[o];
-          acc[4 * o + 0] = fmaf(xv, q.x, acc[4 * o + 0]);
-          acc[4 * o + 1] = fmaf(xv, q.y, acc[4 * o + 1]);
-          acc[4 * o + 2] = fmaf(xv, q.z, acc[4 * o + 2]);
-          acc[4 * o + 3] = fmaf(xv, q.w, acc[4 * o + 3]);
+          acc[2 * o] = __ffma2_rn(xv, make_float2(q.x, q.y), acc[2 * o]);
+          acc[2 * o + 1] = __ffma2_rn(xv, make_float2(q.z, q.w), acc[2 * o + 1]);
         }
       }
   const int oy = oy0 + ty, ox = ox0 + tx;
@@ -236,8 +284,8 @@ stem_conv_kernel(const float* __restrict__ img, const float* __restrict__ w /*[1
 #pragma unroll
     for (int o = 0; o < 16; ++o) {
       const float4 bb = __ldg(reinterpret_cast<const float4*>(bias) + o);
-      d[o] = make_float4(fmaxf(acc[4 * o] + bb.x, 0.f), fmaxf(acc[4 * o + 1] + bb.y, 0.f),
-                         fmaxf(acc[4 * o + 2] + bb.z, 0.f), fmaxf(acc[4 * o + 3] + bb.w, 0.f));
+      d[o] = make_float4(fmaxf(acc[2 * o].x + bb.x, 0.f), fmaxf(acc[2 * o].y + bb.y, 0.f),
+                         fmaxf(acc[2 * o + 1].x + bb.z, 0.f), fmaxf(acc[2 * o + 1].y + bb.w, 0.f));
     }
   }
 }

@@ -25,8 +25,9 @@ constexpr int kBetas = kMaxShape + kMaxExpr;
 constexpr int kPoseFeat = (kJoints - 1) * 9;
 constexpr int kKPad = 448;            // 400 betas + 36 pose features, padded to 7 x 64
 constexpr int kXfFloats = 68;         // per-head transform record (see HeadXf layout below)
-constexpr int kBlendBlockN = 128;
-constexpr int kDecodeChunk = 4096;    // heads per internal pass (bounds the v_posed scratch to ~250 MB)
+constexpr int kBlendBlockN = 128;     // unfused path (v_posed scratch)
+constexpr int kFusedBlockN = 96;      // fused path: 32 vertices per tile
+constexpr int kDecodeChunk = 4096;    // unfused: heads per internal pass (bounds the v_posed scratch to ~250 MB)
 constexpr float kMeshOffsetZ = 0.05f; // flame.py:114
 
 struct FlameLayoutDev {
@@ -189,6 +190,7 @@ flame_prep_kernel(const float* __restrict__ params, int B, FlameLayoutDev L, con
 
 // ------------------------------------------------------------------------------------------------ K2 epilogue
 struct EpiBlend {
+  static constexpr int kExtraSmemBytes = 0;
   struct Params {
     float* out;          // [rows, ld] fp32 v_posed (x,y,z interleaved, n = 3*vertex + coord)
     int ld;
@@ -201,7 +203,7 @@ struct EpiBlend {
     if (cb >= ce) epi_release_tmem(c);
     for (int ch = cb; ch < ce; ++ch) {
       float x[32];
-      epi_load32(c, ch * 32, x);
+      epi_load32<0>(c, ch * 32, x);
       if (ch == ce - 1) epi_release_tmem(c);
       if (!c.valid) continue;
       const int col = c.col0 + ch * 32;
@@ -217,6 +219,144 @@ struct EpiBlend {
         o.w = fmaf(x[4 * j + 3], ep.inv_scale, t.w);
         dst[j] = o;
       }
+    }
+  }
+};
+
+// Fused epilogue: blend-shape accumulator -> template add -> linear-blend skinning -> z offset / 6-DoF rotation (folded
+// into the per-head transforms) -> projection, written straight to the reference's output layouts.  Removes the v_posed
+// round trip (120 KB/head of HBM traffic).  Tile = 128 heads x 32 vertices (block_n = 96); warp (wq, grp) owns heads
+// 32*wq.. and vertices 16*grp.. of the tile.  Per-head transforms sit in shared memory (loaded once per row tile),
+// skinning weights are fetched coalesced and broadcast by shuffles, results are staged per warp so that global stores
+// are contiguous runs (the reference layout's 60 276-byte row pitch rules out TMA stores).
+struct EpiLbs {
+  static constexpr int kXfBytes = 4 * 32 * kXfFloats * 4;          // [lane quarter][32 heads][68]
+  static constexpr int kProjStageBytes = 3328;                      // per warp: 32 rows x 25 floats (+pad)
+  static constexpr int kExtraSmemBytes = kXfBytes + kEpiWarps * kProjStageBytes;
+  struct Params {
+    const float* xf;         // [rows][68] per-head transform records (flame_prep_kernel)
+    const float* weights;    // [nv][5]
+    const float* tmpl;       // [npad]
+    float inv_scale;
+    int nv;
+    float* verts3d;          // [rows][nv][3] or null
+    float* proj;             // [rows][nv][pc] or null
+    int pc;
+    float image_size;
+  };
+
+  static __device__ __forceinline__ void flush(const Params& ep, const EpiCtx& c, const float* vstage, const float* pstage,
+                                               int head0, int vfirst, int rows) {
+    __syncwarp();
+    if (ep.verts3d) {
+#pragma unroll 4
+      for (int it = 0; it < 24; ++it) {
+        const int e = it * 32 + c.lane;
+        const int r = e / 24, cc = e - r * 24;
+        const int h = head0 + r, v = vfirst + cc / 3;
+        if (h < rows && v < ep.nv)
+          ep.verts3d[(static_cast<size_t>(h) * ep.nv + vfirst) * 3 + cc] = vstage[r * 25 + cc];
+      }
+    }
+    if (ep.proj) {
+      if (ep.pc == 2) {
+#pragma unroll 4
+        for (int it = 0; it < 16; ++it) {
+          const int e = it * 32 + c.lane;
+          const int r = e >> 4, cc = e & 15;
+          const int h = head0 + r, v = vfirst + (cc >> 1);
+          if (h < rows && v < ep.nv)
+            ep.proj[(static_cast<size_t>(h) * ep.nv + vfirst) * 2 + cc] = pstage[r * 25 + cc];
+        }
+      } else {
+#pragma unroll 4
+        for (int it = 0; it < 24; ++it) {
+          const int e = it * 32 + c.lane;
+          const int r = e / 24, cc = e - r * 24;
+          const int h = head0 + r, v = vfirst + cc / 3;
+          if (h < rows && v < ep.nv)
+            ep.proj[(static_cast<size_t>(h) * ep.nv + vfirst) * 3 + cc] = pstage[r * 25 + cc];
+        }
+      }
+    }
+    __syncwarp();
+  }
+
+  static __device__ __forceinline__ void run(const Params& ep, const EpiCtx& c) {
+    const int rows = c.g->Wo;
+    const int head0 = c.tc.m_tile * kBlockM + c.wq * 32;
+    float* xf_s = reinterpret_cast<float*>(c.extra) + c.wq * 32 * kXfFloats;
+    float* pstage = reinterpret_cast<float*>(c.extra + kXfBytes + (c.grp * 4 + c.wq) * kProjStageBytes);
+    float* vstage = reinterpret_cast<float*>(c.stage);
+
+    // ---- accumulator -> registers (this warp's 16 vertices = 48 columns), then hand TMEM back
+    float x[48];
+    const int colw = c.grp * 48;
+    epi_load16<0>(c, colw, x);
+    epi_load16<16>(c, colw + 16, x);
+    epi_load16<32>(c, colw + 32, x);
+    epi_release_tmem(c);
+
+    // ---- per-head transforms: once per row tile, shared by the two warps of this lane quarter
+    if (c.tc.m_tile != c.prev_m_tile) {
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + c.wq), "r"(64) : "memory");   // partner is done with the previous row tile
+      const float* src = ep.xf + static_cast<size_t>(head0) * kXfFloats;
+      for (int i = c.lane; i < 32 * kXfFloats; i += 32) {
+        const int r = i / kXfFloats;
+        xf_s[i] = (head0 + r < rows) ? __ldg(&src[i]) : 0.f;                   // both warps write identical values
+      }
+      __syncwarp();
+    }
+
+    // ---- template add (undo the fp16 basis scale), weights for the 16 vertices (coalesced loads, shuffle broadcast)
+    const int col = c.col0 + colw;
+    const int vb = col / 3;                                                     // first vertex of this warp
+    const float t0 = __ldg(&ep.tmpl[col + c.lane]);
+    const float t1 = (c.lane < 16) ? __ldg(&ep.tmpl[col + 32 + c.lane]) : 0.f;
+#pragma unroll
+    for (int j = 0; j < 48; ++j) {
+      const float t = __shfl_sync(0xffffffffu, j < 32 ? t0 : t1, j & 31);
+      x[j] = fmaf(x[j], ep.inv_scale, t);
+    }
+    const int wbase = vb * kJoints, wend = ep.nv * kJoints;
+    const float w0 = (wbase + c.lane < wend) ? __ldg(&ep.weights[wbase + c.lane]) : 0.f;
+    const float w1 = (wbase + 32 + c.lane < wend) ? __ldg(&ep.weights[wbase + 32 + c.lane]) : 0.f;
+    const float w2 = (c.lane < 16 && wbase + 64 + c.lane < wend) ? __ldg(&ep.weights[wbase + 64 + c.lane]) : 0.f;
+
+    const float* xr = xf_s + c.lane * kXfFloats;
+    const float cx = xr[60], cy = xr[61], cz = xr[62], sc = xr[63], tx = xr[64], ty = xr[65];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float px = x[3 * i], py = x[3 * i + 1], pz = x[3 * i + 2];
+      float ox = cx, oy = cy, oz = cz;
+#pragma unroll
+      for (int j = 0; j < kJoints; ++j) {
+        const int idx = 5 * i + j;
+        const float w = __shfl_sync(0xffffffffu, idx < 32 ? w0 : (idx < 64 ? w1 : w2), idx & 31);
+        if (w != 0.f) {                                                          // warp-uniform (same vertex in every lane)
+          const float4 a0 = *reinterpret_cast<const float4*>(xr + 12 * j);
+          const float4 a1 = *reinterpret_cast<const float4*>(xr + 12 * j + 4);
+          const float4 a2 = *reinterpret_cast<const float4*>(xr + 12 * j + 8);
+          ox = fmaf(w, fmaf(a0.x, px, fmaf(a0.y, py, fmaf(a0.z, pz, a0.w))), ox);
+          oy = fmaf(w, fmaf(a1.x, px, fmaf(a1.y, py, fmaf(a1.z, pz, a1.w))), oy);
+          oz = fmaf(w, fmaf(a2.x, px, fmaf(a2.y, py, fmaf(a2.z, pz, a2.w))), oz);
+        }
+      }
+      const int s = (i & 7) * 3;
+      vstage[c.lane * 25 + s] = ox;
+      vstage[c.lane * 25 + s + 1] = oy;
+      vstage[c.lane * 25 + s + 2] = oz;
+      const float qx = ((ox * sc + tx) + 1.0f) * 0.5f * ep.image_size;           // head_mesh.py:40-43
+      const float qy = ((oy * sc + ty) + 1.0f) * 0.5f * ep.image_size;
+      if (ep.pc == 2) {
+        pstage[c.lane * 25 + (i & 7) * 2] = qx;
+        pstage[c.lane * 25 + (i & 7) * 2 + 1] = qy;
+      } else {
+        pstage[c.lane * 25 + s] = qx;
+        pstage[c.lane * 25 + s + 1] = qy;
+        pstage[c.lane * 25 + s + 2] = ((oz * sc + 0.0f) + 1.0f) * 0.5f * ep.image_size;
+      }
+      if ((i & 7) == 7) flush(ep, c, vstage, pstage, head0, vb + (i & 8), rows);
     }
   }
 };
@@ -351,7 +491,9 @@ struct dad3d_flame {
   float* d_weights = nullptr;                // [nv, 5]
   float* d_jt = nullptr;                     // [15]
   float* d_jdirsT = nullptr;                 // [15, 400]
-  CUtensorMap map_b[2];
+  CUtensorMap map_b[2];                      // box 64 x 128 (unfused path)
+  CUtensorMap map_b96[2];                    // box 64 x 96  (fused path)
+  int fused_chunk = 0;                       // heads per pass of the fused path: 4 row tiles per SM
 };
 
 namespace {
@@ -360,12 +502,13 @@ template <class Epi>
 int launch_tile_gemm(const GemmMaps& maps, const GemmGeom& g, const typename Epi::Params& ep, int num_sms,
                      cudaStream_t stream) {
   static int configured_smem = 0;
-  const int smem = gemm_smem_bytes(g);
+  const int smem = gemm_smem_bytes(g, Epi::kExtraSmemBytes);
   if (smem > configured_smem) {
     DAD3D_CUDA_OK(cudaFuncSetAttribute(tile_gemm_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemLimit));
     configured_smem = kGemmSmemLimit;
   }
-  const int total = g.tiles_w * g.tiles_h * g.tiles_n * g.n_tiles;
+  const int m_tiles = g.tiles_w * g.tiles_h * g.tiles_n;
+  const int total = g.sched == 1 ? m_tiles : m_tiles * g.n_tiles;
   const int grid = total < num_sms ? total : num_sms;
   tile_gemm_kernel<Epi><<<grid, kGemmThreads, smem, stream>>>(maps, g, ep);
   count_launch();
@@ -505,7 +648,10 @@ int dad3d_flame_create(dad3d_flame** out, const float* shapedirs_h, const float*
     const uint64_t strides[1] = {static_cast<uint64_t>(kKPad) * 2};
     const uint32_t box[2] = {kBlockK, kBlendBlockN};
     if (!make_tmap_16bit(&h->map_b[p], h->d_basis[p], 2, dims, strides, box, nullptr)) return fail(DAD3D_ERR_CUDA);
+    const uint32_t box96[2] = {kBlockK, kFusedBlockN};
+    if (!make_tmap_16bit(&h->map_b96[p], h->d_basis[p], 2, dims, strides, box96, nullptr)) return fail(DAD3D_ERR_CUDA);
   }
+  h->fused_chunk = h->num_sms * kBlockM * 4;
   *out = h;
   return DAD3D_OK;
 }
@@ -530,8 +676,11 @@ static size_t ws_vposed_bytes(const dad3d_flame* h, int rows) { return align_up(
 
 size_t dad3d_flame_workspace_bytes(const dad3d_flame* h, int32_t B) {
   if (!h || B <= 0) return 0;
-  const int rows = B < kDecodeChunk ? B : kDecodeChunk;
-  return 2 * ws_coef_bytes(rows) + ws_xf_bytes(rows) + ws_vposed_bytes(h, rows) + 1024;
+  const int rows_u = B < kDecodeChunk ? B : kDecodeChunk;                 // unfused / SIMT passes
+  const size_t unfused = 2 * ws_coef_bytes(rows_u) + ws_xf_bytes(rows_u) + ws_vposed_bytes(h, rows_u) + 1024;
+  const int rows_f = B < h->fused_chunk ? B : h->fused_chunk;             // fused passes need no v_posed scratch
+  const size_t fused = 2 * ws_coef_bytes(rows_f) + ws_xf_bytes(rows_f) + 1024;
+  return unfused > fused ? unfused : fused;
 }
 
 int dad3d_flame_decode(dad3d_flame* h, const float* params_d, int32_t B, int32_t flags, float* vertices3d_d,
@@ -544,7 +693,9 @@ int dad3d_flame_decode(dad3d_flame* h, const float* params_d, int32_t B, int32_t
   DAD3D_REQUIRE(workspace_d && workspace_bytes >= dad3d_flame_workspace_bytes(h, B), "workspace too small");
   DAD3D_REQUIRE((reinterpret_cast<uintptr_t>(workspace_d) & 1023) == 0 || true, "workspace alignment");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  const int rows_max = B < kDecodeChunk ? B : kDecodeChunk;
+  const bool fused = !(flags & (DAD3D_BLEND_SIMT | DAD3D_DECODE_UNFUSED));
+  const int chunk = fused ? h->fused_chunk : kDecodeChunk;
+  const int rows_max = B < chunk ? B : chunk;
   uint8_t* ws = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(workspace_d), 1024));
   __half* a_hi = reinterpret_cast<__half*>(ws);
   __half* a_lo = reinterpret_cast<__half*>(ws + ws_coef_bytes(rows_max));
@@ -553,9 +704,11 @@ int dad3d_flame_decode(dad3d_flame* h, const float* params_d, int32_t B, int32_t
   const int pc = to_2d ? 2 : 3;
   const float inv_scale = 1.0f / h->basis_scale;
 
-  for (int b0 = 0; b0 < B; b0 += kDecodeChunk) {
-    const int rows = (B - b0) < kDecodeChunk ? (B - b0) : kDecodeChunk;
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int rows = (B - b0) < chunk ? (B - b0) : chunk;
     const float* p = params_d + static_cast<size_t>(b0) * h->layout.n_params;
+    float* v3 = vertices3d_d ? vertices3d_d + static_cast<size_t>(b0) * h->nv * 3 : nullptr;
+    float* pj = projected_d ? projected_d + static_cast<size_t>(b0) * h->nv * pc : nullptr;
     {
       const int threads = 256;
       const int blocks = ceil_div(rows * 32, threads);
@@ -570,6 +723,7 @@ int dad3d_flame_decode(dad3d_flame* h, const float* params_d, int32_t B, int32_t
       count_launch();
       DAD3D_CUDA_OK(cudaGetLastError());
     } else {
+      const int block_n = fused ? kFusedBlockN : kBlendBlockN;
       GemmMaps maps;
       std::memset(&maps, 0, sizeof(maps));
       __half* planes[2] = {a_hi, a_lo};
@@ -579,7 +733,7 @@ int dad3d_flame_decode(dad3d_flame* h, const float* params_d, int32_t B, int32_t
                                      static_cast<uint64_t>(kKPad) * 2 * rows};
         const uint32_t box[4] = {kBlockK, kBlockM, 1, 1};
         if (!make_tmap_16bit(&maps.a[pi], planes[pi], 4, dims, strides, box, nullptr)) return DAD3D_ERR_CUDA;
-        maps.b[pi] = h->map_b[pi];
+        maps.b[pi] = fused ? h->map_b96[pi] : h->map_b[pi];
       }
       GemmGeom g;
       std::memset(&g, 0, sizeof(g));
@@ -588,8 +742,8 @@ int dad3d_flame_decode(dad3d_flame* h, const float* params_d, int32_t B, int32_t
       g.Wo = rows; g.Ho = 1; g.Nimg = 1;
       g.stride = 1; g.R = 1; g.S = 1; g.pad_h = 0; g.pad_w = 0;
       g.cin_blocks = kKPad / kBlockK;
-      g.n_tiles = h->npad / kBlendBlockN;
-      g.block_n = kBlendBlockN;
+      g.n_tiles = ceil_div(h->n3, block_n);
+      g.block_n = block_n;
       g.fmt16 = 0;
       if (flags & DAD3D_BLEND_FAST) {
         g.nA = 1; g.nB = 1; g.n_mma = 1; g.mma_a[0] = 0; g.mma_b[0] = 0; g.mma_acc[0] = 0; g.n_acc = 1;
@@ -599,15 +753,22 @@ int dad3d_flame_decode(dad3d_flame* h, const float* params_d, int32_t B, int32_t
         g.mma_a[1] = 0; g.mma_b[1] = 1; g.mma_acc[1] = 1;
         g.mma_a[2] = 0; g.mma_b[2] = 0; g.mma_acc[2] = 0;   // hi*hi
       }
-      g.stages = gemm_max_stages(g);
-      EpiBlend::Params ep{vposed, h->npad, h->d_tmpl, inv_scale};
-      int rc = launch_tile_gemm<EpiBlend>(maps, g, ep, h->num_sms, stream);
-      if (rc != DAD3D_OK) return rc;
+      if (fused) {
+        g.sched = g.tiles_w >= h->num_sms ? 1 : 0;          // enough row tiles to give every SM its own
+        g.stages = gemm_max_stages(g, EpiLbs::kExtraSmemBytes);
+        EpiLbs::Params ep{xf, h->d_weights, h->d_tmpl, inv_scale, h->nv, v3, pj, pc, image_size};
+        int rc = launch_tile_gemm<EpiLbs>(maps, g, ep, h->num_sms, stream);
+        if (rc != DAD3D_OK) return rc;
+      } else {
+        g.sched = 0;
+        g.stages = gemm_max_stages(g);
+        EpiBlend::Params ep{vposed, h->npad, h->d_tmpl, inv_scale};
+        int rc = launch_tile_gemm<EpiBlend>(maps, g, ep, h->num_sms, stream);
+        if (rc != DAD3D_OK) return rc;
+      }
     }
-    {
+    if (!fused) {
       dim3 grid(ceil_div(h->nv, kLbsThreads), rows < 1024 ? rows : 1024);
-      float* v3 = vertices3d_d ? vertices3d_d + static_cast<size_t>(b0) * h->nv * 3 : nullptr;
-      float* pj = projected_d ? projected_d + static_cast<size_t>(b0) * h->nv * pc : nullptr;
       lbs_project_kernel<<<grid, kLbsThreads, 0, stream>>>(vposed, h->npad, h->d_weights, xf, rows, h->nv, v3, pj, pc,
                                                            image_size);
       count_launch();

@@ -56,6 +56,10 @@ struct GemmGeom {
   int mma_acc[kMaxMma];            // which accumulator each product goes to (see "accumulator classes" above)
   int stages;                      // smem ring depth
   unsigned fmt16;                  // 0 = fp16, 1 = bf16
+  int sched;                       // 0: tiles round-robin over CTAs with the column tile fastest (default);
+                                   // 1: row-tile persistent -- CTA b owns row tiles b, b+grid, ... and walks ALL column
+                                   //    tiles of each (per-row-tile epilogue state is loaded once; all CTAs sweep the
+                                   //    B operand in step, so it stays hot in L2)
 };
 
 struct GemmMaps {
@@ -67,22 +71,26 @@ struct GemmMaps {
 __host__ __device__ inline int gemm_stage_bytes(const GemmGeom& g) {
   return g.nA * kTileABytes + g.nB * g.block_n * kBlockK * 2;
 }
-__host__ inline int gemm_fixed_smem_bytes() { return kEpiWarps * kStageOutBytes + 1024 /*align slack*/ + 256 /*barriers*/; }
-__host__ inline int gemm_max_stages(const GemmGeom& g) {
-  int s = (kGemmSmemLimit - gemm_fixed_smem_bytes()) / gemm_stage_bytes(g);
+__host__ inline int gemm_fixed_smem_bytes(int extra = 0) {
+  return kEpiWarps * kStageOutBytes + extra + 1024 /*align slack*/ + 256 /*barriers*/;
+}
+__host__ inline int gemm_max_stages(const GemmGeom& g, int extra = 0) {
+  int s = (kGemmSmemLimit - gemm_fixed_smem_bytes(extra)) / gemm_stage_bytes(g);
   return s > 8 ? 8 : s;
 }
-__host__ inline int gemm_smem_bytes(const GemmGeom& g) { return g.stages * gemm_stage_bytes(g) + gemm_fixed_smem_bytes(); }
+__host__ inline int gemm_smem_bytes(const GemmGeom& g, int extra = 0) {
+  return g.stages * gemm_stage_bytes(g) + gemm_fixed_smem_bytes(extra);
+}
 
 struct TileCoord {
   int m_tile, n_tile;
   int n0, h0, w0;   // first output image / row / column of the tile
 };
 
-__device__ __forceinline__ TileCoord decode_tile(const GemmGeom& g, int t) {
+__device__ __forceinline__ TileCoord decode_tile(const GemmGeom& g, int m_tile, int n_tile) {
   TileCoord c;
-  c.n_tile = t % g.n_tiles;
-  c.m_tile = t / g.n_tiles;
+  c.n_tile = n_tile;
+  c.m_tile = m_tile;
   int iw = c.m_tile % g.tiles_w;
   int ih = (c.m_tile / g.tiles_w) % g.tiles_h;
   int in = c.m_tile / (g.tiles_w * g.tiles_h);
@@ -90,6 +98,24 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmGeom& g, int t) {
   c.h0 = ih * g.th;
   c.w0 = iw * g.tw;
   return c;
+}
+
+// i-th tile of this CTA under the geometry's schedule; false when the CTA is out of work
+__device__ __forceinline__ bool tile_at(const GemmGeom& g, int i, TileCoord* tc) {
+  const int m_tiles = g.tiles_w * g.tiles_h * g.tiles_n;
+  int m, n;
+  if (g.sched == 0) {
+    const int t = static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x);
+    if (t >= m_tiles * g.n_tiles) return false;
+    n = t % g.n_tiles;
+    m = t / g.n_tiles;
+  } else {
+    m = static_cast<int>(blockIdx.x) + (i / g.n_tiles) * static_cast<int>(gridDim.x);
+    if (m >= m_tiles) return false;
+    n = i % g.n_tiles;
+  }
+  *tc = decode_tile(g, m, n);
+  return true;
 }
 
 // Everything an epilogue warp needs for one tile.
@@ -102,6 +128,8 @@ struct EpiCtx {
   int lane;
   uint32_t t_acc;    // TMEM address of (lane quarter, accumulator buffer of this tile, accumulator class 0, column 0)
   uint8_t* stage;    // warp-private 4 KiB staging tile (1024-byte aligned)
+  uint8_t* extra;    // Epi::kExtraSmemBytes of CTA-wide shared memory (epilogue-specific use)
+  int prev_m_tile;   // row tile of the previous tile this CTA processed (-1 for the first)
   uint64_t* tempty;  // arrive here (every epilogue thread, once) when the accumulator has been drained into registers
   // this thread's accumulator row
   int n, h, w;
@@ -113,19 +141,39 @@ struct EpiCtx {
 };
 
 // columns [c0, c0+32) of this thread's row, both accumulator classes summed (fp32, round-to-nearest)
-__device__ __forceinline__ void epi_load32(const EpiCtx& c, int c0, float (&x)[32]) {
-  uint32_t v[32];
-  ptx::tmem_ld_32x32b_x32(c.t_acc + static_cast<uint32_t>(c0), v);
+template <int OFF, int N>
+__device__ __forceinline__ void epi_load32(const EpiCtx& c, int c0, float (&x)[N]) {
+  static_assert(OFF + 32 <= N, "slice out of range");
+  float v[32];
+  ptx::tmem_ld_32x32b_x32_f(c.t_acc + static_cast<uint32_t>(c0), v);
   if (c.g->n_acc == 2) {
-    uint32_t v2[32];
-    ptx::tmem_ld_32x32b_x32(c.t_acc + static_cast<uint32_t>(c.g->block_n + c0), v2);
+    float v2[32];
+    ptx::tmem_ld_32x32b_x32_f(c.t_acc + static_cast<uint32_t>(c.g->block_n + c0), v2);
     ptx::tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) + __uint_as_float(v2[j]);
+    for (int j = 0; j < 32; ++j) x[OFF + j] = v[j] + v2[j];
   } else {
     ptx::tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+    for (int j = 0; j < 32; ++j) x[OFF + j] = v[j];
+  }
+}
+// 16 columns [c0, c0+16) into x[OFF..OFF+15]
+template <int OFF, int N>
+__device__ __forceinline__ void epi_load16(const EpiCtx& c, int c0, float (&x)[N]) {
+  static_assert(OFF + 16 <= N, "slice out of range");
+  float v[16];
+  ptx::tmem_ld_32x32b_x16_f(c.t_acc + static_cast<uint32_t>(c0), v);
+  if (c.g->n_acc == 2) {
+    float v2[16];
+    ptx::tmem_ld_32x32b_x16_f(c.t_acc + static_cast<uint32_t>(c.g->block_n + c0), v2);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) x[OFF + j] = v[j] + v2[j];
+  } else {
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) x[OFF + j] = v[j];
   }
 }
 __device__ __forceinline__ void epi_release_tmem(const EpiCtx& c) {
@@ -148,7 +196,8 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stage_bytes = gemm_stage_bytes(g);
   uint8_t* out_stage = smem + g.stages * stage_bytes;                           // [kEpiWarps][4 KiB]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + kEpiWarps * kStageOutBytes);
+  uint8_t* extra_smem = out_stage + kEpiWarps * kStageOutBytes;                 // [Epi::kExtraSmemBytes]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(extra_smem + Epi::kExtraSmemBytes);
   uint64_t* full_bar = bars;                     // [stages]
   uint64_t* empty_bar = bars + g.stages;         // [stages]
   uint64_t* tfull_bar = bars + 2 * g.stages;     // [2]
@@ -157,7 +206,6 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = g.tiles_w * g.tiles_h * g.tiles_n * g.n_tiles;
   const int num_kb = g.R * g.S * g.cin_blocks;
 
   if (warp == 0 && lane == 0) {
@@ -190,8 +238,8 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx_bytes = static_cast<uint32_t>(stage_bytes);
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const TileCoord tc = decode_tile(g, t);
+      TileCoord tc;
+      for (int ti = 0; tile_at(g, ti, &tc); ++ti) {
         for (int kb = 0; kb < num_kb; ++kb) {
           const int tap = kb / g.cin_blocks;
           const int cb = kb - tap * g.cin_blocks;
@@ -221,7 +269,8 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      TileCoord tc_unused;
+      for (int ti = 0; tile_at(g, ti, &tc_unused); ++ti) {
         ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * g.n_acc * g.block_n);
@@ -260,6 +309,8 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
     c.grp = (warp - 4) >> 2;
     c.lane = lane;
     c.stage = out_stage + (warp - 4) * kStageOutBytes;
+    c.extra = extra_smem;
+    c.prev_m_tile = -1;
     const int row = c.wq * 32 + lane;
     const int iw = row % g.tw;
     const int ih = (row / g.tw) % g.th;
@@ -268,8 +319,7 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
     const int biw = row0 % g.tw, bih = (row0 / g.tw) % g.th, bin = row0 / (g.tw * g.th);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      c.tc = decode_tile(g, t);
+    for (int ti = 0; tile_at(g, ti, &c.tc); ++ti) {
       c.n = c.tc.n0 + in;
       c.h = c.tc.h0 + ih;
       c.w = c.tc.w0 + iw;
@@ -284,6 +334,7 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
       ptx::tc_fence_after();
       Epi::run(ep, c);                             // must call epi_release_tmem(c) exactly once per thread
+      c.prev_m_tile = c.tc.m_tile;
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }

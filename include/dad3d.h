@@ -47,6 +47,8 @@ typedef struct dad3d_flame_layout {
 #define DAD3D_BLEND_FAST 4      /* blend-shape product in ONE fp16 tensor-core pass (11-bit operands, like TF32);
                                    default is the 3-product hi/lo split (fp32-class accuracy) */
 #define DAD3D_BLEND_SIMT 8      /* verification aid: blend-shape product on CUDA cores in fp32 (slow) */
+#define DAD3D_DECODE_UNFUSED 16 /* A/B aid: tensor-core blend product to a v_posed scratch + separate skinning kernel
+                                   (default: skinning / rotation / projection fused into the GEMM epilogue) */
 
 DAD3D_API const char* dad3d_last_error(void);
 DAD3D_API int dad3d_version(void);

@@ -127,13 +127,43 @@ def test_general_layout_neck_eyeballs_synthetic(cuda_device):
 
 
 def test_chunk_boundary_and_batch_independence(head_mesh, cuda_device):
-    """B larger than the internal 4096-head pass; every head's result must not depend on its batch (bit-exact)."""
+    """B larger than one internal pass of either path; a head's result must not depend on its batch (bit-exact).
+    The fused path switches to the row-tile-persistent schedule once there are >= #SM row tiles (B >= 148*128)."""
+    dec = head_mesh.flame.decoder(cuda_device)
     B = 4096 + 300
     p = sample_params(B, seed=12).to(cuda_device)
-    v3, pj = head_mesh.decode(p)
     sel = torch.tensor([0, 127, 128, 4095, 4096, 4097, B - 1], device=cuda_device)
-    v_sel, pj_sel = head_mesh.decode(p[sel])
+    for unfused in (False, True):
+        v3, pj = dec.decode(p, want_vertices=True, want_projected=True, unfused=unfused)
+        v_sel, pj_sel = dec.decode(p[sel], want_vertices=True, want_projected=True, unfused=unfused)
+        assert torch.equal(v3[sel], v_sel) and torch.equal(pj[sel], pj_sel)
+    del v3, pj
+    props = torch.cuda.get_device_properties(cuda_device)
+    fused_chunk = props.multi_processor_count * 128 * 4
+    B = fused_chunk + 333                                   # crosses the fused pass boundary, persistent schedule
+    p = sample_params(B, seed=13).to(cuda_device)
+    v3, pj = dec.decode(p, want_vertices=True, want_projected=True)
+    sel = torch.tensor([0, 1, 127, 128, 18943, 18944, fused_chunk - 1, fused_chunk, fused_chunk + 1, B - 1],
+                       device=cuda_device)
+    v_sel, pj_sel = dec.decode(p[sel], want_vertices=True, want_projected=True)
     assert torch.equal(v3[sel], v_sel) and torch.equal(pj[sel], pj_sel)
+    assert torch.isfinite(v3).all()
+
+
+def test_fused_equals_unfused(head_mesh, oracle64, cuda_device):
+    """The fused epilogue (default) and the two-kernel A/B path run the same arithmetic."""
+    dec = head_mesh.flame.decoder(cuda_device)
+    p = sample_params(300, seed=21)
+    for to_2d in (True, False):
+        a = dec.decode(p.to(cuda_device), want_vertices=True, want_projected=True, to_2d=to_2d)
+        b = dec.decode(p.to(cuda_device), want_vertices=True, want_projected=True, to_2d=to_2d, unfused=True)
+        assert (a[0] - b[0]).abs().max().item() < 1e-7 and (a[1] - b[1]).abs().max().item() < 1e-4
+        assert _rel(b[0], oracle64.vertices_3d(p)) < 2e-6
+        assert _rel(a[1], oracle64.reprojected_vertices(p, to_2d=to_2d)) < 2e-6
+    only_v = dec.decode(p.to(cuda_device), want_vertices=True, want_projected=False)
+    only_p = dec.decode(p.to(cuda_device), want_vertices=False, want_projected=True)
+    assert only_v[1] is None and only_p[0] is None
+    assert torch.equal(only_v[0], a[0]) and torch.equal(only_p[1], dec.decode(p.to(cuda_device), want_projected=True)[1])
 
 
 def test_blend_linearity_property(head_mesh, cuda_device):
