@@ -75,6 +75,7 @@ __device__ __forceinline__ void act_store8(uint16_t* base, long long plane, int 
 // ------------------------------------------------------------------------------------------------ conv epilogue
 struct EpiConv {
   static constexpr int kExtraSmemBytes = 0;
+  struct State {};
   struct Params {
     const float* bias;        // [Cout_pad] folded BN shift / conv bias
     int relu;
@@ -219,7 +220,7 @@ struct EpiConv {
     }
   }
 
-  static __device__ __forceinline__ void run(const Params& ep, const EpiCtx& c) {
+  static __device__ __forceinline__ void run(const Params& ep, EpiCtx& c, State&) {
     if (ep.out == nullptr) {
       run_f32(ep, c);
     } else if (c.g->block_n == 128) {
@@ -232,11 +233,13 @@ struct EpiConv {
 
 // ------------------------------------------------------------------------------------------------ stem
 // 7x7 stride-2 pad-3 conv, 3 -> 64 channels, BN folded, ReLU.  in: NCHW fp32 [B,3,H,W]; out: NHWC fp32 [B,H/2,W/2,64].
-// Block = 16x16 output pixels; thread = one pixel, 64 accumulators; weights [147][64] and the 37x37x3 patch in smem.
+// Block = 16x16 output pixels, 256 threads.  Thread = 4 horizontally adjacent pixels x 16 output channels (warp-uniform
+// channel group, so weight reads are shared-memory broadcasts); per (channel, filter row) the 13 input values the 4 pixels
+// need are loaded once and reused across the 7 filter columns.  fp32 math as packed fma.rn.f32x2 (2 FMAs / instruction).
 constexpr int kStemTile = 16;
 constexpr int kStemPatch = kStemTile * 2 + 5;    // 37
 constexpr int kStemSmemBytes = (147 * 64 + 3 * kStemPatch * (kStemPatch + 1)) * 4;
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 stem_conv_kernel(const float* __restrict__ img, const float* __restrict__ w /*[147][64]*/, const float* __restrict__ bias,
                  int H, int W, float* __restrict__ out) {
   extern __shared__ float stem_smem[];            // kStemSmemBytes of dynamic shared memory
@@ -259,33 +262,54 @@ stem_conv_kernel(const float* __restrict__ img, const float* __restrict__ w /*[1
     s_in[c][py][px] = val;
   }
   __syncthreads();
-  const int ty = t / kStemTile, tx = t % kStemTile;
-  // 64 output channels as 32 packed pairs: fma.rn.f32x2 (sm_100) issues two fp32 FMAs per instruction
-  float2 acc[32];
+  const int warp = t >> 5, lane = t & 31;
+  const int cg = warp & 3;                         // 16-channel group, warp-uniform
+  const int quad = (warp >> 2) * 32 + lane;        // 0..63: 4 quads per tile row
+  const int ty = quad >> 2, qx = quad & 3;
+  float2 acc[4][8];
 #pragma unroll
-  for (int o = 0; o < 32; ++o) acc[o] = make_float2(0.f, 0.f);
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int o = 0; o < 8; ++o) acc[p][o] = make_float2(0.f, 0.f);
   for (int c = 0; c < 3; ++c)
-    for (int ky = 0; ky < 7; ++ky)
+#pragma unroll 1
+    for (int ky = 0; ky < 7; ++ky) {
+      float in[13];
+      const float* irow = &s_in[c][ty * 2 + ky][qx * 8];
+#pragma unroll
+      for (int k = 0; k < 13; ++k) in[k] = irow[k];
 #pragma unroll
       for (int kx = 0; kx < 7; ++kx) {
-        const float xs = s_in[c][ty * 2 + ky][tx * 2 + kx];
-        const float2 xv = make_float2(xs, xs);
-        const float4* wr = reinterpret_cast<const float4*>(&s_w[((c * 7 + ky) * 7 + kx) * 64]);
+        const float4* wr = reinterpret_cast<const float4*>(&s_w[((c * 7 + ky) * 7 + kx) * 64 + cg * 16]);
+        const float4 q0 = wr[0], q1 = wr[1], q2 = wr[2], q3 = wr[3];
+        const float2 wv[8] = {make_float2(q0.x, q0.y), make_float2(q0.z, q0.w), make_float2(q1.x, q1.y),
+                              make_float2(q1.z, q1.w), make_float2(q2.x, q2.y), make_float2(q2.z, q2.w),
+                              make_float2(q3.x, q3.y), make_float2(q3.z, q3.w)};
 #pragma unroll
-        for (int o = 0; o < 16; ++o) {
-          const float4 q = wr[o];
-          acc[2 * o] = __ffma2_rn(xv, make_float2(q.x, q.y), acc[2 * o]);
-          acc[2 * o + 1] = __ffma2_rn(xv, make_float2(q.z, q.w), acc[2 * o + 1]);
+        for (int p = 0; p < 4; ++p) {
+          const float xs = in[2 * p + kx];
+          const float2 xv = make_float2(xs, xs);
+#pragma unroll
+          for (int o = 0; o < 8; ++o) acc[p][o] = __ffma2_rn(xv, wv[o], acc[p][o]);
         }
       }
-  const int oy = oy0 + ty, ox = ox0 + tx;
-  if (oy < Ho && ox < Wo) {
-    float4* d = reinterpret_cast<float4*>(out + ((static_cast<size_t>(b) * Ho + oy) * Wo + ox) * 64);
+    }
+  const float4* b4 = reinterpret_cast<const float4*>(bias + cg * 16);
+  const float4 bb0 = __ldg(&b4[0]), bb1 = __ldg(&b4[1]), bb2 = __ldg(&b4[2]), bb3 = __ldg(&b4[3]);
+  const int oy = oy0 + ty;
 #pragma unroll
-    for (int o = 0; o < 16; ++o) {
-      const float4 bb = __ldg(reinterpret_cast<const float4*>(bias) + o);
-      d[o] = make_float4(fmaxf(acc[2 * o].x + bb.x, 0.f), fmaxf(acc[2 * o].y + bb.y, 0.f),
-                         fmaxf(acc[2 * o + 1].x + bb.z, 0.f), fmaxf(acc[2 * o + 1].y + bb.w, 0.f));
+  for (int p = 0; p < 4; ++p) {
+    const int ox = ox0 + qx * 4 + p;
+    if (oy < Ho && ox < Wo) {
+      float4* d = reinterpret_cast<float4*>(out + ((static_cast<size_t>(b) * Ho + oy) * Wo + ox) * 64 + cg * 16);
+      d[0] = make_float4(fmaxf(acc[p][0].x + bb0.x, 0.f), fmaxf(acc[p][0].y + bb0.y, 0.f),
+                         fmaxf(acc[p][1].x + bb0.z, 0.f), fmaxf(acc[p][1].y + bb0.w, 0.f));
+      d[1] = make_float4(fmaxf(acc[p][2].x + bb1.x, 0.f), fmaxf(acc[p][2].y + bb1.y, 0.f),
+                         fmaxf(acc[p][3].x + bb1.z, 0.f), fmaxf(acc[p][3].y + bb1.w, 0.f));
+      d[2] = make_float4(fmaxf(acc[p][4].x + bb2.x, 0.f), fmaxf(acc[p][4].y + bb2.y, 0.f),
+                         fmaxf(acc[p][5].x + bb2.z, 0.f), fmaxf(acc[p][5].y + bb2.w, 0.f));
+      d[3] = make_float4(fmaxf(acc[p][6].x + bb3.x, 0.f), fmaxf(acc[p][6].y + bb3.y, 0.f),
+                         fmaxf(acc[p][7].x + bb3.z, 0.f), fmaxf(acc[p][7].y + bb3.w, 0.f));
     }
   }
 }

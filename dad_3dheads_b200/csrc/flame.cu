@@ -191,13 +191,14 @@ flame_prep_kernel(const float* __restrict__ params, int B, FlameLayoutDev L, con
 // ------------------------------------------------------------------------------------------------ K2 epilogue
 struct EpiBlend {
   static constexpr int kExtraSmemBytes = 0;
+  struct State {};
   struct Params {
     float* out;          // [rows, ld] fp32 v_posed (x,y,z interleaved, n = 3*vertex + coord)
     int ld;
     const float* tmpl;   // [npad] template vertices (fp32, exact)
     float inv_scale;     // undo the power-of-two scaling of the fp16 basis
   };
-  static __device__ __forceinline__ void run(const Params& ep, const EpiCtx& c) {
+  static __device__ __forceinline__ void run(const Params& ep, EpiCtx& c, State&) {
     int cb, ce;
     epi_chunk_range(*c.g, c.grp, &cb, &ce);
     if (cb >= ce) epi_release_tmem(c);
@@ -226,13 +227,13 @@ struct EpiBlend {
 // Fused epilogue: blend-shape accumulator -> template add -> linear-blend skinning -> z offset / 6-DoF rotation (folded
 // into the per-head transforms) -> projection, written straight to the reference's output layouts.  Removes the v_posed
 // round trip (120 KB/head of HBM traffic).  Tile = 128 heads x 32 vertices (block_n = 96); warp (wq, grp) owns heads
-// 32*wq.. and vertices 16*grp.. of the tile.  Per-head transforms sit in shared memory (loaded once per row tile),
-// skinning weights are fetched coalesced and broadcast by shuffles, results are staged per warp so that global stores
-// are contiguous runs (the reference layout's 60 276-byte row pitch rules out TMA stores).
+// 32*wq.. and vertices 16*grp.. of the tile, processed as two passes of 8 vertices (24 accumulator columns).
+// The thread's per-head transforms (5 x 3x4 + offsets) live in REGISTERS and are reloaded only when the row tile changes
+// (once per 157 tiles under the row-tile-persistent schedule); skinning weights are fetched coalesced and broadcast by
+// shuffles; results are staged per warp so that global stores are contiguous runs (the reference layout's 60 276-byte
+// row pitch rules out TMA stores).
 struct EpiLbs {
-  static constexpr int kXfBytes = 4 * 32 * kXfFloats * 4;          // [lane quarter][32 heads][68]
-  static constexpr int kProjStageBytes = 3328;                      // per warp: 32 rows x 25 floats (+pad)
-  static constexpr int kExtraSmemBytes = kXfBytes + kEpiWarps * kProjStageBytes;
+  static constexpr int kExtraSmemBytes = 0;
   struct Params {
     const float* xf;         // [rows][68] per-head transform records (flame_prep_kernel)
     const float* weights;    // [nv][5]
@@ -244,119 +245,140 @@ struct EpiLbs {
     int pc;
     float image_size;
   };
+  // per-thread state that survives across tiles (lives in the kernel's epilogue loop via EpiCtx::user)
+  struct State {
+    float A[kJoints][12];
+    float cx, cy, cz, sc, tx, ty;
+  };
 
-  static __device__ __forceinline__ void flush(const Params& ep, const EpiCtx& c, const float* vstage, const float* pstage,
-                                               int head0, int vfirst, int rows) {
+  // write the warp's staged [32 rows][ncol floats] (row pitch 25) as contiguous runs of `ncol` floats per head row.
+  // NCOL is 24 (8 vertices x 3) or 16 (8 vertices x 2): 4 rows x NCOL floats = NCOL/8 full warp stores.
+  template <int NCOL>
+  static __device__ __forceinline__ void flush(float* __restrict__ dst, size_t row_pitch, const float* stage, int lane,
+                                               int head0, int rows, int n_valid_cols) {
     __syncwarp();
-    if (ep.verts3d) {
-#pragma unroll 4
-      for (int it = 0; it < 24; ++it) {
-        const int e = it * 32 + c.lane;
-        const int r = e / 24, cc = e - r * 24;
-        const int h = head0 + r, v = vfirst + cc / 3;
-        if (h < rows && v < ep.nv)
-          ep.verts3d[(static_cast<size_t>(h) * ep.nv + vfirst) * 3 + cc] = vstage[r * 25 + cc];
-      }
-    }
-    if (ep.proj) {
-      if (ep.pc == 2) {
-#pragma unroll 4
-        for (int it = 0; it < 16; ++it) {
-          const int e = it * 32 + c.lane;
-          const int r = e >> 4, cc = e & 15;
-          const int h = head0 + r, v = vfirst + (cc >> 1);
-          if (h < rows && v < ep.nv)
-            ep.proj[(static_cast<size_t>(h) * ep.nv + vfirst) * 2 + cc] = pstage[r * 25 + cc];
-        }
-      } else {
-#pragma unroll 4
-        for (int it = 0; it < 24; ++it) {
-          const int e = it * 32 + c.lane;
-          const int r = e / 24, cc = e - r * 24;
-          const int h = head0 + r, v = vfirst + cc / 3;
-          if (h < rows && v < ep.nv)
-            ep.proj[(static_cast<size_t>(h) * ep.nv + vfirst) * 3 + cc] = pstage[r * 25 + cc];
+    constexpr int kPer = NCOL / 8;                 // warp stores per group of 4 rows
+#pragma unroll
+    for (int s = 0; s < kPer; ++s) {
+      const int e = s * 32 + lane;                 // position inside a 4-row group
+      const int rr = e / NCOL, cc = e - rr * NCOL; // constants per (s, lane)
+      if (cc < n_valid_cols) {
+#pragma unroll
+        for (int rg = 0; rg < 8; ++rg) {
+          const int r = rg * 4 + rr;
+          if (head0 + r < rows) dst[static_cast<size_t>(r) * row_pitch + cc] = stage[r * 25 + cc];
         }
       }
     }
     __syncwarp();
   }
 
-  static __device__ __forceinline__ void run(const Params& ep, const EpiCtx& c) {
+  static __device__ __forceinline__ void run(const Params& ep, EpiCtx& c, State& st) {
     const int rows = c.g->Wo;
     const int head0 = c.tc.m_tile * kBlockM + c.wq * 32;
-    float* xf_s = reinterpret_cast<float*>(c.extra) + c.wq * 32 * kXfFloats;
-    float* pstage = reinterpret_cast<float*>(c.extra + kXfBytes + (c.grp * 4 + c.wq) * kProjStageBytes);
-    float* vstage = reinterpret_cast<float*>(c.stage);
+    float* stage = reinterpret_cast<float*>(c.stage);
 
-    // ---- accumulator -> registers (this warp's 16 vertices = 48 columns), then hand TMEM back
-    float x[48];
-    const int colw = c.grp * 48;
-    epi_load16<0>(c, colw, x);
-    epi_load16<16>(c, colw + 16, x);
-    epi_load16<32>(c, colw + 32, x);
-    epi_release_tmem(c);
-
-    // ---- per-head transforms: once per row tile, shared by the two warps of this lane quarter
+    // ---- per-head transforms -> registers, once per row tile
     if (c.tc.m_tile != c.prev_m_tile) {
-      asm volatile("bar.sync %0, %1;" ::"r"(1 + c.wq), "r"(64) : "memory");   // partner is done with the previous row tile
-      const float* src = ep.xf + static_cast<size_t>(head0) * kXfFloats;
-      for (int i = c.lane; i < 32 * kXfFloats; i += 32) {
-        const int r = i / kXfFloats;
-        xf_s[i] = (head0 + r < rows) ? __ldg(&src[i]) : 0.f;                   // both warps write identical values
+      const int h = min(head0 + c.lane, rows - 1);
+      const float4* src = reinterpret_cast<const float4*>(ep.xf + static_cast<size_t>(h) * kXfFloats);
+#pragma unroll
+      for (int j = 0; j < kJoints; ++j) {
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          const float4 v = __ldg(&src[3 * j + q]);
+          st.A[j][4 * q] = v.x; st.A[j][4 * q + 1] = v.y; st.A[j][4 * q + 2] = v.z; st.A[j][4 * q + 3] = v.w;
+        }
       }
-      __syncwarp();
+      const float4 u = __ldg(&src[15]);
+      const float4 w = __ldg(&src[16]);
+      st.cx = u.x; st.cy = u.y; st.cz = u.z; st.sc = u.w; st.tx = w.x; st.ty = w.y;
     }
 
-    // ---- template add (undo the fp16 basis scale), weights for the 16 vertices (coalesced loads, shuffle broadcast)
+    const int colw = c.grp * 48;
     const int col = c.col0 + colw;
     const int vb = col / 3;                                                     // first vertex of this warp
+    // template values and skinning weights of the warp's 16 vertices: coalesced loads, broadcast later by shuffles
     const float t0 = __ldg(&ep.tmpl[col + c.lane]);
     const float t1 = (c.lane < 16) ? __ldg(&ep.tmpl[col + 32 + c.lane]) : 0.f;
-#pragma unroll
-    for (int j = 0; j < 48; ++j) {
-      const float t = __shfl_sync(0xffffffffu, j < 32 ? t0 : t1, j & 31);
-      x[j] = fmaf(x[j], ep.inv_scale, t);
-    }
     const int wbase = vb * kJoints, wend = ep.nv * kJoints;
     const float w0 = (wbase + c.lane < wend) ? __ldg(&ep.weights[wbase + c.lane]) : 0.f;
     const float w1 = (wbase + 32 + c.lane < wend) ? __ldg(&ep.weights[wbase + 32 + c.lane]) : 0.f;
     const float w2 = (c.lane < 16 && wbase + 64 + c.lane < wend) ? __ldg(&ep.weights[wbase + 64 + c.lane]) : 0.f;
 
-    const float* xr = xf_s + c.lane * kXfFloats;
-    const float cx = xr[60], cy = xr[61], cz = xr[62], sc = xr[63], tx = xr[64], ty = xr[65];
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      // ---- 24 accumulator columns (8 vertices) of this pass, both accumulator classes
+      float x[24];
+      {
+        const uint32_t t = c.t_acc + static_cast<uint32_t>(colw + pass * 24);
+        const bool two = c.g->n_acc == 2;
+        float a[16], b[16];
+        ptx::tmem_ld_32x32b_x16_f(t, a);
+        if (two) ptx::tmem_ld_32x32b_x16_f(t + c.g->block_n, b);
+        ptx::tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const float px = x[3 * i], py = x[3 * i + 1], pz = x[3 * i + 2];
-      float ox = cx, oy = cy, oz = cz;
+        for (int j = 0; j < 16; ++j) x[j] = two ? a[j] + b[j] : a[j];
+        ptx::tmem_ld_32x32b_x8_f(t + 16, a);
+        if (two) ptx::tmem_ld_32x32b_x8_f(t + c.g->block_n + 16, b);
+        ptx::tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < kJoints; ++j) {
-        const int idx = 5 * i + j;
-        const float w = __shfl_sync(0xffffffffu, idx < 32 ? w0 : (idx < 64 ? w1 : w2), idx & 31);
-        if (w != 0.f) {                                                          // warp-uniform (same vertex in every lane)
-          const float4 a0 = *reinterpret_cast<const float4*>(xr + 12 * j);
-          const float4 a1 = *reinterpret_cast<const float4*>(xr + 12 * j + 4);
-          const float4 a2 = *reinterpret_cast<const float4*>(xr + 12 * j + 8);
-          ox = fmaf(w, fmaf(a0.x, px, fmaf(a0.y, py, fmaf(a0.z, pz, a0.w))), ox);
-          oy = fmaf(w, fmaf(a1.x, px, fmaf(a1.y, py, fmaf(a1.z, pz, a1.w))), oy);
-          oz = fmaf(w, fmaf(a2.x, px, fmaf(a2.y, py, fmaf(a2.z, pz, a2.w))), oz);
+        for (int j = 0; j < 8; ++j) x[16 + j] = two ? a[j] + b[j] : a[j];
+      }
+      if (pass == 1) epi_release_tmem(c);
+#pragma unroll
+      for (int j = 0; j < 24; ++j) {
+        const int jj = pass * 24 + j;
+        const float t = __shfl_sync(0xffffffffu, jj < 32 ? t0 : t1, jj & 31);
+        x[j] = fmaf(x[j], ep.inv_scale, t);                                     // undo basis scale, add template
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float px = x[3 * i], py = x[3 * i + 1], pz = x[3 * i + 2];
+        float ox = st.cx, oy = st.cy, oz = st.cz;
+#pragma unroll
+        for (int j = 0; j < kJoints; ++j) {
+          const int idx = 5 * (pass * 8 + i) + j;
+          const float w = __shfl_sync(0xffffffffu, idx < 32 ? w0 : (idx < 64 ? w1 : w2), idx & 31);
+          if (w != 0.f) {                                                        // warp-uniform: same vertex in every lane
+            ox = fmaf(w, fmaf(st.A[j][0], px, fmaf(st.A[j][1], py, fmaf(st.A[j][2], pz, st.A[j][3]))), ox);
+            oy = fmaf(w, fmaf(st.A[j][4], px, fmaf(st.A[j][5], py, fmaf(st.A[j][6], pz, st.A[j][7]))), oy);
+            oz = fmaf(w, fmaf(st.A[j][8], px, fmaf(st.A[j][9], py, fmaf(st.A[j][10], pz, st.A[j][11]))), oz);
+          }
+        }
+        x[3 * i] = ox; x[3 * i + 1] = oy; x[3 * i + 2] = oz;
+      }
+      const int vfirst = vb + pass * 8;
+      const int nvalid = min(8, ep.nv - vfirst);                                // vertices of this pass inside the mesh
+      if (nvalid > 0) {
+        if (ep.verts3d) {
+#pragma unroll
+          for (int j = 0; j < 24; ++j) stage[c.lane * 25 + j] = x[j];
+          flush<24>(ep.verts3d + (static_cast<size_t>(head0) * ep.nv + vfirst) * 3, static_cast<size_t>(ep.nv) * 3, stage,
+                    c.lane, head0, rows, nvalid * 3);
+        }
+        if (ep.proj) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float qx = ((x[3 * i] * st.sc + st.tx) + 1.0f) * 0.5f * ep.image_size;       // head_mesh.py:40-43
+            const float qy = ((x[3 * i + 1] * st.sc + st.ty) + 1.0f) * 0.5f * ep.image_size;
+            if (ep.pc == 2) {
+              stage[c.lane * 25 + 2 * i] = qx;
+              stage[c.lane * 25 + 2 * i + 1] = qy;
+            } else {
+              stage[c.lane * 25 + 3 * i] = qx;
+              stage[c.lane * 25 + 3 * i + 1] = qy;
+              stage[c.lane * 25 + 3 * i + 2] = ((x[3 * i + 2] * st.sc + 0.0f) + 1.0f) * 0.5f * ep.image_size;
+            }
+          }
+          if (ep.pc == 2)
+            flush<16>(ep.proj + (static_cast<size_t>(head0) * ep.nv + vfirst) * 2, static_cast<size_t>(ep.nv) * 2, stage,
+                      c.lane, head0, rows, nvalid * 2);
+          else
+            flush<24>(ep.proj + (static_cast<size_t>(head0) * ep.nv + vfirst) * 3, static_cast<size_t>(ep.nv) * 3, stage,
+                      c.lane, head0, rows, nvalid * 3);
         }
       }
-      const int s = (i & 7) * 3;
-      vstage[c.lane * 25 + s] = ox;
-      vstage[c.lane * 25 + s + 1] = oy;
-      vstage[c.lane * 25 + s + 2] = oz;
-      const float qx = ((ox * sc + tx) + 1.0f) * 0.5f * ep.image_size;           // head_mesh.py:40-43
-      const float qy = ((oy * sc + ty) + 1.0f) * 0.5f * ep.image_size;
-      if (ep.pc == 2) {
-        pstage[c.lane * 25 + (i & 7) * 2] = qx;
-        pstage[c.lane * 25 + (i & 7) * 2 + 1] = qy;
-      } else {
-        pstage[c.lane * 25 + s] = qx;
-        pstage[c.lane * 25 + s + 1] = qy;
-        pstage[c.lane * 25 + s + 2] = ((oz * sc + 0.0f) + 1.0f) * 0.5f * ep.image_size;
-      }
-      if ((i & 7) == 7) flush(ep, c, vstage, pstage, head0, vb + (i & 8), rows);
     }
   }
 };

@@ -167,6 +167,14 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16_f(uint32_t taddr, float* r) {
       : "r"(taddr)
       : "memory");
 }
+// 32 lanes x 8 columns
+__device__ __forceinline__ void tmem_ld_32x32b_x8_f(uint32_t taddr, float* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
+      : "r"(taddr)
+      : "memory");
+}
 // warpgroup-wide register re-budgeting (all 4 warps of the warpgroup must execute it)
 template <int N>
 __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }

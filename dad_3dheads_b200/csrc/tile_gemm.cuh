@@ -302,6 +302,7 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
     }
   } else if (warp >= 4) {
     // ===================================================== epilogue warps
+    typename Epi::State user_state;                // per-thread state that persists across this CTA's tiles
     EpiCtx c;
     c.g = &g;
     c.maps = &maps;
@@ -333,7 +334,7 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
       c.t_acc = tmem_base + (static_cast<uint32_t>(c.wq * 32) << 16) + static_cast<uint32_t>(acc * g.n_acc * g.block_n);
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
       ptx::tc_fence_after();
-      Epi::run(ep, c);                             // must call epi_release_tmem(c) exactly once per thread
+      Epi::run(ep, c, user_state);                 // must call epi_release_tmem(c) exactly once per thread
       c.prev_m_tile = c.tc.m_tile;
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
