@@ -4,6 +4,7 @@
 // linear layer as an implicit GEMM on tcgen05) + encoder_kernels.cuh (stem, pooling, BiFPN sums, fusion concat, heads).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -110,6 +111,7 @@ struct dad3d_encoder {
   float bifpn_w[2][20];            // per block: w1 normalised [2][4] then w2 normalised [3][4]
   std::unique_ptr<Plan> plan;
   size_t ws_cache_B = 0, ws_cache_bytes = 0;
+  bool use_pdl = true;             // programmatic dependent launch for the tile-engine kernels (env DAD3D_NO_PDL=1 disables)
   bool debug_keep_all = false;     // disable buffer reuse so every activation can be read back after a forward
   // live profiling of the dominant kernel (bench.py roofline): CUDA events around every tile_gemm launch
   bool profile = false;
@@ -483,7 +485,19 @@ int launch_conv(dad3d_encoder* enc, const Step& s, cudaStream_t stream) {
     enc->prof_flops += conv_useful_flops(s);
     DAD3D_CUDA_OK(cudaEventRecord(ev->first, stream));
   }
-  tile_gemm_kernel<EpiConv><<<grid, kGemmThreads, gemm_smem_bytes(g), stream>>>(s.maps, g, s.epi);
+  {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = gemm_smem_bytes(g);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = enc->use_pdl ? 1 : 0;
+    DAD3D_CUDA_OK(cudaLaunchKernelEx(&cfg, tile_gemm_kernel<EpiConv>, s.maps, g, s.epi));
+  }
   count_launch();
   if (ev) DAD3D_CUDA_OK(cudaEventRecord(ev->second, stream));
   DAD3D_CUDA_OK(cudaGetLastError());
@@ -523,6 +537,10 @@ int dad3d_encoder_create(dad3d_encoder** out, const dad3d_conv_weights* layers, 
     for (int i = 0; i < 6; ++i) { enc->mma_a[i] = pa[i]; enc->mma_b[i] = pb[i]; enc->mma_acc[i] = pc[i]; }
   }
   std::memcpy(enc->bifpn_w, bifpn_fusion_w_h, sizeof(enc->bifpn_w));
+  {
+    const char* e = std::getenv("DAD3D_NO_PDL");
+    enc->use_pdl = !(e && e[0] == '1');
+  }
 
   auto fail = [&](int code) { dad3d_encoder_destroy(enc.release()); return code; };
   for (int li = 0; li < n_layers; ++li) {

@@ -23,7 +23,9 @@ constexpr int kMaxShape = 300;        // flame.py:107
 constexpr int kMaxExpr = 100;         // flame.py:108
 constexpr int kBetas = kMaxShape + kMaxExpr;
 constexpr int kPoseFeat = (kJoints - 1) * 9;
-constexpr int kKPad = 448;            // 400 betas + 36 pose features, padded to 7 x 64
+constexpr int kKPad = 448;            // 400 betas + 36 pose features + 1 template column, padded to 7 x 64
+constexpr int kTmplCol = kBetas + kPoseFeat;   // two columns with coefficient 1.0 carry the (scaled) template exactly,
+                                               // so the GEMM itself adds it
 constexpr int kXfFloats = 68;         // per-head transform record (see HeadXf layout below)
 constexpr int kBlendBlockN = 128;     // unfused path (v_posed scratch)
 constexpr int kFusedBlockN = 96;      // fused path: 32 vertices per tile
@@ -78,8 +80,8 @@ __device__ __forceinline__ void split_store(__half* hi, __half* lo, size_t idx, 
 
 __global__ void __launch_bounds__(256)
 flame_prep_kernel(const float* __restrict__ params, int B, FlameLayoutDev L, const float* __restrict__ jt,
-                  const float* __restrict__ jdirsT, int flags, __half* __restrict__ a_hi, __half* __restrict__ a_lo,
-                  float* __restrict__ xf) {
+                  const float* __restrict__ jdirsT, int flags, float inv_scale, __half* __restrict__ a_hi,
+                  __half* __restrict__ a_lo, float* __restrict__ xf) {
   const int h = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (h >= B) return;
@@ -100,8 +102,8 @@ flame_prep_kernel(const float* __restrict__ params, int B, FlameLayoutDev L, con
 #pragma unroll
     for (int j = 0; j < 15; ++j) acc[j] = fmaf(b, __ldg(&jdirsT[j * kBetas + l]), acc[j]);
   }
-  for (int l = kBetas + kPoseFeat + lane; l < kKPad; l += 32) {
-    a_hi[arow + l] = __float2half_rn(0.f);
+  for (int l = kTmplCol + lane; l < kKPad; l += 32) {     // template column gets coefficient 1, the rest is padding
+    a_hi[arow + l] = __float2half_rn(l < kTmplCol + 2 ? 1.f : 0.f);
     a_lo[arow + l] = __float2half_rn(0.f);
   }
 #pragma unroll
@@ -173,10 +175,10 @@ flame_prep_kernel(const float* __restrict__ params, int B, FlameLayoutDev L, con
     for (int k = 0; k < 3; ++k) t[k] = Gt[i][k] - rj[k];
     mat3_mul(R6, GR[i], AR);
     mat3_vec(R6, t, At);
-    for (int r = 0; r < 3; ++r) {
-      o[i * 12 + r * 4 + 0] = AR[3 * r + 0];
-      o[i * 12 + r * 4 + 1] = AR[3 * r + 1];
-      o[i * 12 + r * 4 + 2] = AR[3 * r + 2];
+    for (int r = 0; r < 3; ++r) {          // rotation part absorbs 1/basis_scale (exact power of two): it is applied
+      o[i * 12 + r * 4 + 0] = AR[3 * r + 0] * inv_scale;   // to the still-scaled GEMM output
+      o[i * 12 + r * 4 + 1] = AR[3 * r + 1] * inv_scale;
+      o[i * 12 + r * 4 + 2] = AR[3 * r + 2] * inv_scale;
       o[i * 12 + r * 4 + 3] = At[r];
     }
   }
@@ -193,10 +195,8 @@ struct EpiBlend {
   static constexpr int kExtraSmemBytes = 0;
   struct State {};
   struct Params {
-    float* out;          // [rows, ld] fp32 v_posed (x,y,z interleaved, n = 3*vertex + coord)
+    float* out;          // [rows, ld] fp32 v_posed * basis_scale (x,y,z interleaved, n = 3*vertex + coord)
     int ld;
-    const float* tmpl;   // [npad] template vertices (fp32, exact)
-    float inv_scale;     // undo the power-of-two scaling of the fp16 basis
   };
   static __device__ __forceinline__ void run(const Params& ep, EpiCtx& c, State&) {
     int cb, ce;
@@ -207,61 +207,49 @@ struct EpiBlend {
       epi_load32<0>(c, ch * 32, x);
       if (ch == ce - 1) epi_release_tmem(c);
       if (!c.valid) continue;
-      const int col = c.col0 + ch * 32;
-      float4* dst = reinterpret_cast<float4*>(ep.out + static_cast<size_t>(c.pix) * ep.ld + col);
-      const float4* t4 = reinterpret_cast<const float4*>(ep.tmpl + col);
+      float4* dst = reinterpret_cast<float4*>(ep.out + static_cast<size_t>(c.pix) * ep.ld + c.col0 + ch * 32);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 t = __ldg(&t4[j]);
-        float4 o;
-        o.x = fmaf(x[4 * j + 0], ep.inv_scale, t.x);
-        o.y = fmaf(x[4 * j + 1], ep.inv_scale, t.y);
-        o.z = fmaf(x[4 * j + 2], ep.inv_scale, t.z);
-        o.w = fmaf(x[4 * j + 3], ep.inv_scale, t.w);
-        dst[j] = o;
-      }
+      for (int j = 0; j < 8; ++j) dst[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
     }
   }
 };
 
-// Fused epilogue: blend-shape accumulator -> template add -> linear-blend skinning -> z offset / 6-DoF rotation (folded
-// into the per-head transforms) -> projection, written straight to the reference's output layouts.  Removes the v_posed
-// round trip (120 KB/head of HBM traffic).  Tile = 128 heads x 32 vertices (block_n = 96); warp (wq, grp) owns heads
-// 32*wq.. and vertices 16*grp.. of the tile, processed as two passes of 8 vertices (24 accumulator columns).
-// The thread's per-head transforms (5 x 3x4 + offsets) live in REGISTERS and are reloaded only when the row tile changes
-// (once per 157 tiles under the row-tile-persistent schedule); skinning weights are fetched coalesced and broadcast by
-// shuffles; results are staged per warp so that global stores are contiguous runs (the reference layout's 60 276-byte
-// row pitch rules out TMA stores).
+// Fused epilogue (layouts without neck / eyeball pose, i.e. the released model): blend-shape accumulator (template
+// included, still scaled) -> linear-blend skinning -> z offset / 6-DoF rotation (folded into the per-head transforms) ->
+// projection, written straight to the reference's output layouts.  Removes the v_posed round trip (120 KB/head).
+// With only the jaw posed, the transforms of the other four joints coincide, so skinning needs two transforms per head
+// (rest = joint 0, jaw = joint 2: 30 floats, register-resident) and two weights per vertex (w_rest = sum of the non-jaw
+// weights, w_jaw).  Tile = 128 heads x 32 vertices (block_n = 96); warp (wq, grp) owns heads 32*wq.. and vertices
+// 16*grp.. of the tile, as two passes of 8 vertices (24 accumulator columns).  Results are staged per warp so that global
+// stores are contiguous runs (the reference layout's 60 276-byte row pitch rules out TMA stores).
 struct EpiLbs {
   static constexpr int kExtraSmemBytes = 0;
   struct Params {
     const float* xf;         // [rows][68] per-head transform records (flame_prep_kernel)
-    const float* weights;    // [nv][5]
-    const float* tmpl;       // [npad]
-    float inv_scale;
+    const float* w2;         // [nv][2]  (w_rest, w_jaw)
     int nv;
     float* verts3d;          // [rows][nv][3] or null
     float* proj;             // [rows][nv][pc] or null
     int pc;
     float image_size;
   };
-  // per-thread state that survives across tiles (lives in the kernel's epilogue loop via EpiCtx::user)
-  struct State {
-    float A[kJoints][12];
+  struct State {             // per-thread, persists across the tiles of a row tile
+    float R[12];             // rest transform  [R | t] rows (rotation pre-divided by the basis scale)
+    float Jw[12];            // jaw transform
     float cx, cy, cz, sc, tx, ty;
   };
 
-  // write the warp's staged [32 rows][ncol floats] (row pitch 25) as contiguous runs of `ncol` floats per head row.
-  // NCOL is 24 (8 vertices x 3) or 16 (8 vertices x 2): 4 rows x NCOL floats = NCOL/8 full warp stores.
+  // write the warp's staged [32 rows][NCOL floats] (row pitch 25) as contiguous runs of NCOL floats per head row:
+  // 4 rows x NCOL floats = NCOL/8 full warp stores; (rr, cc) depend only on (s, lane).
   template <int NCOL>
   static __device__ __forceinline__ void flush(float* __restrict__ dst, size_t row_pitch, const float* stage, int lane,
                                                int head0, int rows, int n_valid_cols) {
     __syncwarp();
-    constexpr int kPer = NCOL / 8;                 // warp stores per group of 4 rows
+    constexpr int kPer = NCOL / 8;
 #pragma unroll
     for (int s = 0; s < kPer; ++s) {
-      const int e = s * 32 + lane;                 // position inside a 4-row group
-      const int rr = e / NCOL, cc = e - rr * NCOL; // constants per (s, lane)
+      const int e = s * 32 + lane;
+      const int rr = e / NCOL, cc = e - rr * NCOL;
       if (cc < n_valid_cols) {
 #pragma unroll
         for (int rg = 0; rg < 8; ++rg) {
@@ -278,17 +266,15 @@ struct EpiLbs {
     const int head0 = c.tc.m_tile * kBlockM + c.wq * 32;
     float* stage = reinterpret_cast<float*>(c.stage);
 
-    // ---- per-head transforms -> registers, once per row tile
-    if (c.tc.m_tile != c.prev_m_tile) {
+    if (c.tc.m_tile != c.prev_m_tile) {            // per-head transforms -> registers, once per row tile
       const int h = min(head0 + c.lane, rows - 1);
       const float4* src = reinterpret_cast<const float4*>(ep.xf + static_cast<size_t>(h) * kXfFloats);
 #pragma unroll
-      for (int j = 0; j < kJoints; ++j) {
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-          const float4 v = __ldg(&src[3 * j + q]);
-          st.A[j][4 * q] = v.x; st.A[j][4 * q + 1] = v.y; st.A[j][4 * q + 2] = v.z; st.A[j][4 * q + 3] = v.w;
-        }
+      for (int q = 0; q < 3; ++q) {
+        const float4 a = __ldg(&src[q]);           // joint 0
+        const float4 b = __ldg(&src[6 + q]);       // joint 2 (jaw)
+        st.R[4 * q] = a.x; st.R[4 * q + 1] = a.y; st.R[4 * q + 2] = a.z; st.R[4 * q + 3] = a.w;
+        st.Jw[4 * q] = b.x; st.Jw[4 * q + 1] = b.y; st.Jw[4 * q + 2] = b.z; st.Jw[4 * q + 3] = b.w;
       }
       const float4 u = __ldg(&src[15]);
       const float4 w = __ldg(&src[16]);
@@ -296,20 +282,13 @@ struct EpiLbs {
     }
 
     const int colw = c.grp * 48;
-    const int col = c.col0 + colw;
-    const int vb = col / 3;                                                     // first vertex of this warp
-    // template values and skinning weights of the warp's 16 vertices: coalesced loads, broadcast later by shuffles
-    const float t0 = __ldg(&ep.tmpl[col + c.lane]);
-    const float t1 = (c.lane < 16) ? __ldg(&ep.tmpl[col + 32 + c.lane]) : 0.f;
-    const int wbase = vb * kJoints, wend = ep.nv * kJoints;
-    const float w0 = (wbase + c.lane < wend) ? __ldg(&ep.weights[wbase + c.lane]) : 0.f;
-    const float w1 = (wbase + 32 + c.lane < wend) ? __ldg(&ep.weights[wbase + 32 + c.lane]) : 0.f;
-    const float w2 = (c.lane < 16 && wbase + 64 + c.lane < wend) ? __ldg(&ep.weights[wbase + 64 + c.lane]) : 0.f;
+    const int vb = (c.col0 + colw) / 3;                                          // first vertex of this warp
+    // (w_rest, w_jaw) of the warp's 16 vertices: one coalesced load, broadcast by shuffles
+    const float wl = (vb * 2 + c.lane < ep.nv * 2) ? __ldg(&ep.w2[vb * 2 + c.lane]) : 0.f;
 
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
-      // ---- 24 accumulator columns (8 vertices) of this pass, both accumulator classes
-      float x[24];
+      float x[24];                                                               // 8 vertices of this pass
       {
         const uint32_t t = c.t_acc + static_cast<uint32_t>(colw + pass * 24);
         const bool two = c.g->n_acc == 2;
@@ -327,29 +306,22 @@ struct EpiLbs {
       }
       if (pass == 1) epi_release_tmem(c);
 #pragma unroll
-      for (int j = 0; j < 24; ++j) {
-        const int jj = pass * 24 + j;
-        const float t = __shfl_sync(0xffffffffu, jj < 32 ? t0 : t1, jj & 31);
-        x[j] = fmaf(x[j], ep.inv_scale, t);                                     // undo basis scale, add template
-      }
-#pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float px = x[3 * i], py = x[3 * i + 1], pz = x[3 * i + 2];
-        float ox = st.cx, oy = st.cy, oz = st.cz;
-#pragma unroll
-        for (int j = 0; j < kJoints; ++j) {
-          const int idx = 5 * (pass * 8 + i) + j;
-          const float w = __shfl_sync(0xffffffffu, idx < 32 ? w0 : (idx < 64 ? w1 : w2), idx & 31);
-          if (w != 0.f) {                                                        // warp-uniform: same vertex in every lane
-            ox = fmaf(w, fmaf(st.A[j][0], px, fmaf(st.A[j][1], py, fmaf(st.A[j][2], pz, st.A[j][3]))), ox);
-            oy = fmaf(w, fmaf(st.A[j][4], px, fmaf(st.A[j][5], py, fmaf(st.A[j][6], pz, st.A[j][7]))), oy);
-            oz = fmaf(w, fmaf(st.A[j][8], px, fmaf(st.A[j][9], py, fmaf(st.A[j][10], pz, st.A[j][11]))), oz);
-          }
-        }
-        x[3 * i] = ox; x[3 * i + 1] = oy; x[3 * i + 2] = oz;
+        const float wr = __shfl_sync(0xffffffffu, wl, 2 * (pass * 8 + i));
+        const float wj = __shfl_sync(0xffffffffu, wl, 2 * (pass * 8 + i) + 1);
+        const float rx = fmaf(st.R[0], px, fmaf(st.R[1], py, fmaf(st.R[2], pz, st.R[3])));
+        const float ry = fmaf(st.R[4], px, fmaf(st.R[5], py, fmaf(st.R[6], pz, st.R[7])));
+        const float rz = fmaf(st.R[8], px, fmaf(st.R[9], py, fmaf(st.R[10], pz, st.R[11])));
+        const float jx = fmaf(st.Jw[0], px, fmaf(st.Jw[1], py, fmaf(st.Jw[2], pz, st.Jw[3])));
+        const float jy = fmaf(st.Jw[4], px, fmaf(st.Jw[5], py, fmaf(st.Jw[6], pz, st.Jw[7])));
+        const float jz = fmaf(st.Jw[8], px, fmaf(st.Jw[9], py, fmaf(st.Jw[10], pz, st.Jw[11])));
+        x[3 * i] = fmaf(wj, jx, fmaf(wr, rx, st.cx));
+        x[3 * i + 1] = fmaf(wj, jy, fmaf(wr, ry, st.cy));
+        x[3 * i + 2] = fmaf(wj, jz, fmaf(wr, rz, st.cz));
       }
       const int vfirst = vb + pass * 8;
-      const int nvalid = min(8, ep.nv - vfirst);                                // vertices of this pass inside the mesh
+      const int nvalid = min(8, ep.nv - vfirst);                                 // vertices of this pass inside the mesh
       if (nvalid > 0) {
         if (ep.verts3d) {
 #pragma unroll
@@ -386,8 +358,7 @@ struct EpiLbs {
 // verification aid (DAD3D_BLEND_SIMT): same product on CUDA cores from the same hi/lo planes
 __global__ void blend_simt_kernel(const __half* __restrict__ a_hi, const __half* __restrict__ a_lo,
                                   const __half* __restrict__ b_hi, const __half* __restrict__ b_lo,
-                                  const float* __restrict__ tmpl, float inv_scale, int rows, int npad,
-                                  float* __restrict__ out) {
+                                  int rows, int npad, float* __restrict__ out) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   const int h = blockIdx.y;
   if (n >= npad || h >= rows) return;
@@ -397,7 +368,7 @@ __global__ void blend_simt_kernel(const __half* __restrict__ a_hi, const __half*
     const float b = __half2float(b_hi[static_cast<size_t>(n) * kKPad + k]) + __half2float(b_lo[static_cast<size_t>(n) * kKPad + k]);
     acc = fmaf(a, b, acc);
   }
-  out[static_cast<size_t>(h) * npad + n] = fmaf(acc, inv_scale, tmpl[n]);
+  out[static_cast<size_t>(h) * npad + n] = acc;            // scaled v_posed (template column included)
 }
 
 // ------------------------------------------------------------------------------------------------ K3
@@ -509,7 +480,8 @@ struct dad3d_flame {
   FlameLayoutDev layout{};
   float basis_scale = 1.f;
   __half* d_basis[2] = {nullptr, nullptr};   // [npad, kKPad] fp16 hi / lo planes of scale * [shapedirs | posedirs^T]
-  float* d_tmpl = nullptr;                   // [npad]
+  float* d_w2 = nullptr;                     // [nv, 2] (sum of non-jaw weights, jaw weight) for the fused path
+  bool jaw_only = false;                     // layout has no neck / eyeball pose -> fused epilogue is exact
   float* d_weights = nullptr;                // [nv, 5]
   float* d_jt = nullptr;                     // [15]
   float* d_jdirsT = nullptr;                 // [15, 400]
@@ -606,12 +578,19 @@ int dad3d_flame_create(dad3d_flame** out, const float* shapedirs_h, const float*
   float amax = 0.f;
   for (size_t i = 0; i < static_cast<size_t>(n3) * kBetas; ++i) amax = fmaxf(amax, fabsf(shapedirs_h[i]));
   for (size_t i = 0; i < static_cast<size_t>(kPoseFeat) * n3; ++i) amax = fmaxf(amax, fabsf(posedirs_h[i]));
+  float tmax = 0.f;
+  for (int i = 0; i < n3; ++i) tmax = fmaxf(tmax, fabsf(v_template_h[i]));
   int e = 0;
   if (amax > 0.f) {
     std::frexp(amax, &e);          // amax = m * 2^e, m in [0.5,1)
     e = 10 - e;                     // scaled amax in [512, 1024)
     if (e > 24) e = 24;
     if (e < -8) e = -8;
+  }
+  if (tmax > 0.f) {                 // the template rides in the same fp16 planes: keep scale * |T| below 2^15
+    int et = 0;
+    std::frexp(tmax, &et);
+    if (e > 15 - et) e = 15 - et;
   }
   h->basis_scale = std::ldexp(1.0f, e);
 
@@ -626,9 +605,28 @@ int dad3d_flame_create(dad3d_flame** out, const float* shapedirs_h, const float*
       rh[k] = hb;
       rl[k] = f32_to_f16_bits(x - f16_bits_to_f32(hb));
     }
+    // template: two columns with coefficient 1 (kTmplCol, kTmplCol+1 -- the prep kernel writes 1.0 into both):
+    // column 0 carries hi/lo of scale*T, column 1 the hi/lo of what is left, so the sum is exact in fp32
+    float r = v_template_h[n] * h->basis_scale;
+    for (int k = 0; k < 2; ++k) {
+      const unsigned short hb = f32_to_f16_bits(r);
+      r -= f16_bits_to_f32(hb);
+      const unsigned short lb = f32_to_f16_bits(r);
+      r -= f16_bits_to_f32(lb);
+      rh[kTmplCol + k] = hb;
+      rl[kTmplCol + k] = lb;
+    }
   }
-  std::vector<float> tmpl(npad, 0.f);
-  for (int n = 0; n < n3; ++n) tmpl[n] = v_template_h[n];
+  // (sum of the non-jaw weights, jaw weight) per vertex for the jaw-only fused epilogue
+  std::vector<float> w2(static_cast<size_t>(n_vertices) * 2, 0.f);
+  for (int i = 0; i < n_vertices; ++i) {
+    float rest = 0.f;
+    for (int j = 0; j < kJoints; ++j)
+      if (j != 2) rest += lbs_weights_h[static_cast<size_t>(i) * kJoints + j];
+    w2[2 * i] = rest;
+    w2[2 * i + 1] = lbs_weights_h[static_cast<size_t>(i) * kJoints + 2];
+  }
+  h->jaw_only = (lay->neck == 0 && lay->eyeballs == 0);
 
   // folded joint regressor: J = Jreg * T + (Jreg * S) beta   (smplx vertices2joints applied to v_shaped)
   std::vector<float> jt(15, 0.f), jdirsT(15 * kBetas, 0.f);
@@ -654,13 +652,13 @@ int dad3d_flame_create(dad3d_flame** out, const float* shapedirs_h, const float*
   const size_t plane = static_cast<size_t>(npad) * kKPad * sizeof(__half);
   CK(cudaMalloc(&h->d_basis[0], plane));
   CK(cudaMalloc(&h->d_basis[1], plane));
-  CK(cudaMalloc(&h->d_tmpl, npad * sizeof(float)));
+  CK(cudaMalloc(&h->d_w2, w2.size() * sizeof(float)));
   CK(cudaMalloc(&h->d_weights, static_cast<size_t>(n_vertices) * kJoints * sizeof(float)));
   CK(cudaMalloc(&h->d_jt, 15 * sizeof(float)));
   CK(cudaMalloc(&h->d_jdirsT, 15 * kBetas * sizeof(float)));
   CK(cudaMemcpy(h->d_basis[0], hi.data(), plane, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(h->d_basis[1], lo.data(), plane, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(h->d_tmpl, tmpl.data(), npad * sizeof(float), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->d_w2, w2.data(), w2.size() * sizeof(float), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(h->d_weights, lbs_weights_h, static_cast<size_t>(n_vertices) * kJoints * sizeof(float), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(h->d_jt, jt.data(), 15 * sizeof(float), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(h->d_jdirsT, jdirsT.data(), 15 * kBetas * sizeof(float), cudaMemcpyHostToDevice));
@@ -682,7 +680,7 @@ void dad3d_flame_destroy(dad3d_flame* h) {
   if (!h) return;
   cudaFree(h->d_basis[0]);
   cudaFree(h->d_basis[1]);
-  cudaFree(h->d_tmpl);
+  cudaFree(h->d_w2);
   cudaFree(h->d_weights);
   cudaFree(h->d_jt);
   cudaFree(h->d_jdirsT);
@@ -715,7 +713,7 @@ int dad3d_flame_decode(dad3d_flame* h, const float* params_d, int32_t B, int32_t
   DAD3D_REQUIRE(workspace_d && workspace_bytes >= dad3d_flame_workspace_bytes(h, B), "workspace too small");
   DAD3D_REQUIRE((reinterpret_cast<uintptr_t>(workspace_d) & 1023) == 0 || true, "workspace alignment");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  const bool fused = !(flags & (DAD3D_BLEND_SIMT | DAD3D_DECODE_UNFUSED));
+  const bool fused = h->jaw_only && !(flags & (DAD3D_BLEND_SIMT | DAD3D_DECODE_UNFUSED));
   const int chunk = fused ? h->fused_chunk : kDecodeChunk;
   const int rows_max = B < chunk ? B : chunk;
   uint8_t* ws = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(workspace_d), 1024));
@@ -734,14 +732,14 @@ int dad3d_flame_decode(dad3d_flame* h, const float* params_d, int32_t B, int32_t
     {
       const int threads = 256;
       const int blocks = ceil_div(rows * 32, threads);
-      flame_prep_kernel<<<blocks, threads, 0, stream>>>(p, rows, h->layout, h->d_jt, h->d_jdirsT, flags, a_hi, a_lo, xf);
+      flame_prep_kernel<<<blocks, threads, 0, stream>>>(p, rows, h->layout, h->d_jt, h->d_jdirsT, flags, inv_scale, a_hi,
+                                                        a_lo, xf);
       count_launch();
       DAD3D_CUDA_OK(cudaGetLastError());
     }
     if (flags & DAD3D_BLEND_SIMT) {
       dim3 grid(ceil_div(h->npad, 256), rows);
-      blend_simt_kernel<<<grid, 256, 0, stream>>>(a_hi, a_lo, h->d_basis[0], h->d_basis[1], h->d_tmpl, inv_scale, rows,
-                                                  h->npad, vposed);
+      blend_simt_kernel<<<grid, 256, 0, stream>>>(a_hi, a_lo, h->d_basis[0], h->d_basis[1], rows, h->npad, vposed);
       count_launch();
       DAD3D_CUDA_OK(cudaGetLastError());
     } else {
@@ -778,13 +776,13 @@ int dad3d_flame_decode(dad3d_flame* h, const float* params_d, int32_t B, int32_t
       if (fused) {
         g.sched = g.tiles_w >= h->num_sms ? 1 : 0;          // enough row tiles to give every SM its own
         g.stages = gemm_max_stages(g, EpiLbs::kExtraSmemBytes);
-        EpiLbs::Params ep{xf, h->d_weights, h->d_tmpl, inv_scale, h->nv, v3, pj, pc, image_size};
+        EpiLbs::Params ep{xf, h->d_w2, h->nv, v3, pj, pc, image_size};
         int rc = launch_tile_gemm<EpiLbs>(maps, g, ep, h->num_sms, stream);
         if (rc != DAD3D_OK) return rc;
       } else {
         g.sched = 0;
         g.stages = gemm_max_stages(g);
-        EpiBlend::Params ep{vposed, h->npad, h->d_tmpl, inv_scale};
+        EpiBlend::Params ep{vposed, h->npad};
         int rc = launch_tile_gemm<EpiBlend>(maps, g, ep, h->num_sms, stream);
         if (rc != DAD3D_OK) return rc;
       }

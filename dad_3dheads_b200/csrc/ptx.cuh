@@ -67,6 +67,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// wait: block until the preceding grid in the stream has completed and its memory is visible (no-op when the kernel was
+// launched without the programmatic-serialization attribute).  launch_dependents: allow the next grid to start early.
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- fences
 __device__ __forceinline__ void fence_proxy_async_smem() {   // generic-proxy smem writes -> visible to async proxy (TMA/UMMA)
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

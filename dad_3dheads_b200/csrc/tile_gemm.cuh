@@ -17,9 +17,9 @@
 // products go to accumulator 0 and all the small correction products to accumulator 1; the epilogue adds the two in
 // fp32 with round-to-nearest.  That cuts the number of truncating steps on the large accumulator by n_mma (6x / 3x).
 //
-// Roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one lane), warp 2 = TMEM allocator, warps 4..11 =
-// epilogue: warp w owns TMEM lanes 32*(w%4).. (accumulator rows) and column group (w-4)/4 (half of the tile's columns),
-// i.e. two epilogue warps per SM sub-partition so their dependent-issue stalls overlap.
+// Roles (320 threads): warp 0 = TMEM allocator + TMA producer (one lane), warp 1 = barrier init + MMA issuer (one lane),
+// warps 2..9 = epilogue: warp w owns TMEM lanes 32*(w%4).. (accumulator rows) and column group (w-2)/4 (half of the
+// tile's columns), i.e. two epilogue warps per SM sub-partition so their dependent-issue stalls overlap.
 // Pipelines: smem ring (full/empty mbarriers) between TMA and MMA; two TMEM accumulator buffers (tmem_full/tmem_empty)
 // between MMA and epilogue, so the epilogue of tile i overlaps the main loop of tile i+1.  Each epilogue warp owns a
 // 4 KiB shared-memory staging tile from which it issues TMA stores of its 32 rows x (32|64) channels.
@@ -34,7 +34,8 @@ constexpr int kTileABytes = kBlockM * kBlockK * 2;   // 16 KiB per A piece per s
 constexpr int kMaxPieces = 3;
 constexpr int kMaxMma = 6;
 constexpr int kEpiWarps = 8;
-constexpr int kGemmThreads = 128 + kEpiWarps * 32;   // 384
+constexpr int kFirstEpiWarp = 2;
+constexpr int kGemmThreads = (kFirstEpiWarp + kEpiWarps) * 32;   // 320 -> up to 200 registers per thread
 constexpr int kTmemCols = 512;
 constexpr int kStageOutBytes = 4096;              // per epilogue warp: 32 rows x 128 B
 constexpr int kGemmSmemLimit = 227 * 1024;
@@ -189,7 +190,7 @@ __device__ __forceinline__ void epi_chunk_range(const GemmGeom& g, int grp, int*
 }
 
 template <class Epi>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __maxnreg__(200)
 tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const typename Epi::Params ep) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle atoms (TMA writes and UMMA reads must agree on the pattern).
@@ -223,7 +224,7 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
     }
     ptx::fence_mbar_init();
   }
-  if (warp == 2) {
+  if (warp == 0) {
     ptx::tmem_alloc(tmem_slot, kTmemCols);
     ptx::tmem_relinquish();
   }
@@ -231,6 +232,10 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) may overlap the previous kernel's tail;
+  // nothing below may touch global memory before the previous grid has fully completed.
+  ptx::grid_dep_launch();
+  ptx::grid_dep_wait();
 
   if (warp == 0) {
     // ===================================================== TMA producer
@@ -300,16 +305,16 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
         if (acc == 0) acc_phase ^= 1u;
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= kFirstEpiWarp) {
     // ===================================================== epilogue warps
     typename Epi::State user_state;                // per-thread state that persists across this CTA's tiles
     EpiCtx c;
     c.g = &g;
     c.maps = &maps;
     c.wq = warp & 3;
-    c.grp = (warp - 4) >> 2;
+    c.grp = (warp - kFirstEpiWarp) >> 2;
     c.lane = lane;
-    c.stage = out_stage + (warp - 4) * kStageOutBytes;
+    c.stage = out_stage + (warp - kFirstEpiWarp) * kStageOutBytes;
     c.extra = extra_smem;
     c.prev_m_tile = -1;
     const int row = c.wq * 32 + lane;
@@ -344,7 +349,7 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == 0) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, kTmemCols);
   }
