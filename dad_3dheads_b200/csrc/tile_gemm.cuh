@@ -35,7 +35,7 @@ constexpr int kMaxPieces = 3;
 constexpr int kMaxMma = 6;
 constexpr int kEpiWarps = 8;
 constexpr int kFirstEpiWarp = 2;
-constexpr int kGemmThreads = (kFirstEpiWarp + kEpiWarps) * 32;   // 320 -> up to 200 registers per thread
+constexpr int kGemmThreads = (kFirstEpiWarp + kEpiWarps) * 32;   // 320 threads x 192 registers (warp allocation granularity 512) = 61440 <= 64 K
 constexpr int kTmemCols = 512;
 constexpr int kStageOutBytes = 4096;              // per epilogue warp: 32 rows x 128 B
 constexpr int kGemmSmemLimit = 227 * 1024;
@@ -190,11 +190,13 @@ __device__ __forceinline__ void epi_chunk_range(const GemmGeom& g, int grp, int*
 }
 
 template <class Epi>
-__global__ void __maxnreg__(200)
+__global__ void __maxnreg__(192)
 tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const typename Epi::Params ep) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle atoms (TMA writes and UMMA reads must agree on the pattern).
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // (pointer arithmetic on smem_raw -- not an integer round-trip -- so the compiler keeps the shared address space and
+  //  emits LDS/STS instead of generic LD/ST for everything derived from it)
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   const int stage_bytes = gemm_stage_bytes(g);
   uint8_t* out_stage = smem + g.stages * stage_bytes;                           // [kEpiWarps][4 KiB]
   uint8_t* extra_smem = out_stage + kEpiWarps * kStageOutBytes;                 // [Epi::kExtraSmemBytes]
