@@ -34,7 +34,9 @@ struct ConvW {
   int cout_pad = 0, cin_pad = 0, block_n = 0;
   uint16_t* d_w = nullptr;      // [P][cout_pad][R*S*cin_pad] bf16 pieces
   float* d_bias = nullptr;      // [cout_pad]
-  CUtensorMap map_b[kMaxPieces];
+  CUtensorMap map_b[kMaxPieces];      // box 64 x block_n
+  CUtensorMap map_b64[kMaxPieces];    // box 64 x 64 (small problems: more, narrower tiles to fill the SMs)
+  bool has_b64 = false;
 };
 
 int pick_block_n(int cout) {
@@ -388,8 +390,12 @@ int make_plan(dad3d_encoder* enc, int B, void* ws, size_t ws_bytes, bool layout_
     g.stride = s.stride;
     g.R = w->R; g.S = w->S; g.pad_h = s.pad; g.pad_w = s.pad;
     g.cin_blocks = w->cin_pad / kBlockK;
-    g.block_n = w->block_n;
-    g.n_tiles = w->cout_pad / w->block_n;
+    // few row tiles (small maps / small batch): halve the tile width so that twice as many CTAs share the work
+    const int m_tiles = g.tiles_w * g.tiles_h * g.tiles_n;
+    const bool narrow = w->has_b64 && m_tiles * (w->cout_pad / w->block_n) * 2 <= enc->num_sms;
+    const int block_n = narrow ? 64 : w->block_n;
+    g.block_n = block_n;
+    g.n_tiles = w->cout_pad / block_n;
     g.nA = enc->P; g.nB = enc->P;
     g.n_mma = enc->n_mma;
     g.n_acc = enc->n_acc;
@@ -407,7 +413,7 @@ int make_plan(dad3d_encoder* enc, int B, void* ws, size_t ws_bytes, bool layout_
       const uint32_t es[4] = {1, static_cast<uint32_t>(s.stride), static_cast<uint32_t>(s.stride), 1};
       const uint16_t* basep = reinterpret_cast<const uint16_t*>(ti.ptr) + static_cast<size_t>(p) * ti.plane_elems();
       if (!make_tmap_16bit(&s.maps.a[p], basep, 4, dims, strides, box, es)) return DAD3D_ERR_CUDA;
-      s.maps.b[p] = w->map_b[p];
+      s.maps.b[p] = narrow ? w->map_b64[p] : w->map_b[p];
     }
     EpiConv::Params& ep = s.epi;
     std::memset(&ep, 0, sizeof(ep));
@@ -425,12 +431,12 @@ int make_plan(dad3d_encoder* enc, int B, void* ws, size_t ws_bytes, bool layout_
       ep.out_plane = to.plane_elems();
       ep.out_planes = to.planes;
       ep.ld_out = to.C;
-      if (w->block_n != 64 && w->block_n != 128) {
+      if (block_n != 64 && block_n != 128) {
         set_error("layer " + w->name + ": piece outputs need block_n 64 or 128");
         return DAD3D_ERR_INVALID;
       }
-      // per-warp store box: 32 consecutive tile rows = (bw x bh x bn) output pixels, block_n/2 channels
-      const int nc = w->block_n / 2;
+      // per-warp store box: 32 consecutive tile rows = (bw x bh x bn) output pixels x 32 channels (SWIZZLE_64B rows)
+      const int nc = 32;
       const int bw = std::min(g.tw, 32);
       const int bh = std::min(g.th, 32 / bw);
       const int bn = 32 / (bw * bh);
@@ -602,6 +608,14 @@ int dad3d_encoder_create(dad3d_encoder** out, const dad3d_conv_weights* layers, 
       if (!make_tmap_16bit(&cw.map_b[p], cw.d_w + p * plane, 2, dims, strides, box, nullptr)) {
         cudaFree(cw.d_w); cudaFree(cw.d_bias);
         return fail(DAD3D_ERR_CUDA);
+      }
+      if (cw.block_n == 128) {
+        const uint32_t box64[2] = {kBlockK, 64};
+        if (!make_tmap_16bit(&cw.map_b64[p], cw.d_w + p * plane, 2, dims, strides, box64, nullptr)) {
+          cudaFree(cw.d_w); cudaFree(cw.d_bias);
+          return fail(DAD3D_ERR_CUDA);
+        }
+        cw.has_b64 = true;
       }
     }
     enc->convs[name] = cw;

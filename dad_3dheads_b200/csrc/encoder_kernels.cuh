@@ -75,7 +75,9 @@ __device__ __forceinline__ void act_store8(uint16_t* base, long long plane, int 
 // ------------------------------------------------------------------------------------------------ conv epilogue
 struct EpiConv {
   static constexpr int kExtraSmemBytes = 0;
-  struct State {};
+  struct State {
+    float r[64];              // residual / gate operand of the current tile (this thread's row, this warp's columns)
+  };
   struct Params {
     const float* bias;        // [Cout_pad] folded BN shift / conv bias
     int relu;
@@ -115,92 +117,89 @@ struct EpiConv {
   // piece outputs: NC = block_n / 2 columns per warp (32 or 64).  The warp's 32 rows x NC channels are staged in its
   // private shared-memory tile in the TMA swizzle pattern and written with ONE bulk tensor store per piece plane
   // (out-of-range rows of partial tiles are clipped by the tensor map).
-  template <int NC>
-  static __device__ __forceinline__ void run_pieces(const Params& ep, const EpiCtx& c) {
-    float x[NC];
-    const int colw = c.grp * NC;                      // first column of this warp inside the tile
-    epi_load32<0>(c, colw, x);
-    if constexpr (NC == 64) epi_load32<32>(c, colw + 32, x);
-    epi_release_tmem(c);
-    const int col = c.col0 + colw;
+  // The warp's columns are handled in halves of 32 channels (block_n 128 -> two halves per warp, block_n 64 -> one), which
+  // keeps the per-thread working set at 32 accumulator values (+ the prefetched residual).  Staging rows are 64 bytes
+  // (TMA SWIZZLE_64B pattern: 16-byte chunk index XOR ((row >> 1) & 3)).
+  static __device__ __forceinline__ int halves(const EpiCtx& c) { return c.g->block_n / 64; }
+  static __device__ __forceinline__ int first_col(const EpiCtx& c, int half) {
+    return c.grp * (c.g->block_n / 2) + half * 32;            // column inside the tile
+  }
+
+  // Residual / gate operand: the warp's 32 rows x 32 channels per piece plane, loaded BEFORE the accumulator is awaited
+  // so the latency hides behind the tile's main loop.  Loads are cooperative (a warp instruction covers whole 64-byte
+  // row segments -> 8 memory wavefronts instead of 32 for per-thread rows), transposed through the staging tile; every
+  // lane then reads back its own row and sums the pieces (smallest first).
+  template <int H>
+  static __device__ __forceinline__ void prefetch_half(const Params& ep, const EpiCtx& c, State& st) {
+    const int swz = (c.lane >> 1) & 3;
+    const uint8_t* rowp = c.stage + c.lane * 64;
+    const int col = c.col0 + first_col(c, H);
+    if (c.lane == 0) ptx::bulk_wait_read0();          // an earlier TMA store may still be reading the staging tile
+    __syncwarp();
 #pragma unroll
-    for (int j = 0; j < NC / 4; ++j) {
+    for (int j = 0; j < 32; ++j) st.r[H * 32 + j] = 0.f;
+    for (int p = ep.res.planes - 1; p >= 0; --p) {
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int idx = it * 32 + c.lane;
+        const int row = idx >> 2, seg = idx & 3;
+        const long long spix = __shfl_sync(0xffffffffu, c.pix, row);
+        const int svalid = __shfl_sync(0xffffffffu, c.valid ? 1 : 0, row);
+        uint4 q = make_uint4(0, 0, 0, 0);
+        if (svalid) q = __ldg(reinterpret_cast<const uint4*>(ep.res.base + p * ep.res.plane + spix * ep.res.C + col + seg * 8));
+        *reinterpret_cast<uint4*>(c.stage + row * 64 + ((seg ^ ((row >> 1) & 3)) << 4)) = q;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const uint4 q = *reinterpret_cast<const uint4*>(rowp + ((q4 ^ swz) << 4));
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          st.r[H * 32 + 8 * q4 + 2 * j] += __uint_as_float(w[j] << 16);
+          st.r[H * 32 + 8 * q4 + 2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+        }
+      }
+      __syncwarp();
+    }
+  }
+
+  static __device__ __forceinline__ void prefetch(const Params& ep, EpiCtx& c, State& st) {
+    if (ep.res_mode == 0 || ep.out == nullptr) return;
+    prefetch_half<0>(ep, c, st);
+    if (halves(c) == 2) prefetch_half<1>(ep, c, st);
+  }
+
+  template <int H>
+  static __device__ __forceinline__ void run_half(const Params& ep, const EpiCtx& c, State& st, bool last) {
+    float x[32];
+    const int colt = first_col(c, H);
+    epi_load32<0>(c, colt, x);
+    if (last) epi_release_tmem(c);
+    const int col = c.col0 + colt;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
       const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col) + j);
       x[4 * j] += b.x; x[4 * j + 1] += b.y; x[4 * j + 2] += b.z; x[4 * j + 3] += b.w;
     }
-    constexpr int kRowBytes = NC * 2;                 // 64 (SWIZZLE_64B) or 128 (SWIZZLE_128B)
-    const int swz = (NC == 64) ? (c.lane & 7) : ((c.lane >> 1) & 3);
-    uint8_t* rowp = c.stage + c.lane * kRowBytes;
-    if (ep.res_mode != 0) {
-      // Residual / gate operand: the warp's 32 rows x NC channels per piece plane.  Loaded COOPERATIVELY (each warp
-      // instruction covers whole 64/128-byte row segments -> 4-8 memory wavefronts instead of 32 for per-thread rows),
-      // transposed through the staging tile (same swizzle as the output path), then every lane reads back its own row.
-      constexpr int kSegs = NC / 8;                   // 16-byte segments per row
-      if (c.lane == 0) ptx::bulk_wait_read0();        // the previous tile's last store may still be reading the tile
-      __syncwarp();
-      auto stage_plane = [&](int p) {
+    if (ep.res_mode == 1) {
 #pragma unroll
-        for (int it = 0; it < kSegs; ++it) {
-          const int idx = it * 32 + c.lane;
-          const int row = idx / kSegs, seg = idx % kSegs;
-          const long long spix = __shfl_sync(0xffffffffu, c.pix, row);
-          const int svalid = __shfl_sync(0xffffffffu, c.valid ? 1 : 0, row);
-          uint4 q = make_uint4(0, 0, 0, 0);
-          if (svalid) q = __ldg(reinterpret_cast<const uint4*>(ep.res.base + p * ep.res.plane + spix * ep.res.C + col + seg * 8));
-          const int rswz = (NC == 64) ? (row & 7) : ((row >> 1) & 3);
-          *reinterpret_cast<uint4*>(c.stage + row * kRowBytes + ((seg ^ rswz) << 4)) = q;
-        }
-        __syncwarp();
-      };
-      if (ep.res_mode == 1) {                         // ResUnit: x += identity (pieces added smallest first)
-        for (int p = ep.res.planes - 1; p >= 0; --p) {
-          stage_plane(p);
+      for (int j = 0; j < 32; ++j) x[j] += st.r[H * 32 + j];
+    } else if (ep.res_mode == 2) {
 #pragma unroll
-          for (int q8 = 0; q8 < kSegs; ++q8) {
-            const uint4 q = *reinterpret_cast<const uint4*>(rowp + ((q8 ^ swz) << 4));
-            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              x[8 * q8 + 2 * j] += __uint_as_float(w[j] << 16);
-              x[8 * q8 + 2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
-            }
-          }
-          __syncwarp();
-        }
-      } else {                                        // FusionLayer gate: x *= (p0 + p1 + p2), 32 columns at a time
-#pragma unroll
-        for (int half = 0; half < NC / 32; ++half) {
-          float rs[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) rs[j] = 0.f;
-          for (int p = ep.res.planes - 1; p >= 0; --p) {
-            stage_plane(p);
-#pragma unroll
-            for (int q8 = 0; q8 < 4; ++q8) {
-              const uint4 q = *reinterpret_cast<const uint4*>(rowp + (((half * 4 + q8) ^ swz) << 4));
-              const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                rs[8 * q8 + 2 * j] += __uint_as_float(w[j] << 16);
-                rs[8 * q8 + 2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
-              }
-            }
-            __syncwarp();
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) x[half * 32 + j] *= rs[j];
-        }
-      }
+      for (int j = 0; j < 32; ++j) x[j] *= st.r[H * 32 + j];
     }
     if (ep.relu) {
 #pragma unroll
-      for (int j = 0; j < NC; ++j) x[j] = fmaxf(x[j], 0.f);
+      for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
     }
+    const int swz = (c.lane >> 1) & 3;
+    uint8_t* rowp = c.stage + c.lane * 64;
     for (int p = 0; p < ep.out_planes; ++p) {
       if (c.lane == 0) ptx::bulk_wait_read0();        // previous store has finished reading the staging tile
       __syncwarp();
 #pragma unroll
-      for (int q = 0; q < NC / 8; ++q) {              // 16-byte chunks of this row
+      for (int q = 0; q < 4; ++q) {                   // 16-byte chunks of this row
         uint32_t w[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -220,13 +219,14 @@ struct EpiConv {
     }
   }
 
-  static __device__ __forceinline__ void run(const Params& ep, EpiCtx& c, State&) {
+  static __device__ __forceinline__ void run(const Params& ep, EpiCtx& c, State& st) {
     if (ep.out == nullptr) {
       run_f32(ep, c);
-    } else if (c.g->block_n == 128) {
-      run_pieces<64>(ep, c);
+    } else if (halves(c) == 2) {
+      run_half<0>(ep, c, st, false);
+      run_half<1>(ep, c, st, true);
     } else {
-      run_pieces<32>(ep, c);
+      run_half<0>(ep, c, st, true);
     }
   }
 };

@@ -198,6 +198,7 @@ struct EpiBlend {
     float* out;          // [rows, ld] fp32 v_posed * basis_scale (x,y,z interleaved, n = 3*vertex + coord)
     int ld;
   };
+  static __device__ __forceinline__ void prefetch(const Params&, EpiCtx&, State&) {}
   static __device__ __forceinline__ void run(const Params& ep, EpiCtx& c, State&) {
     int cb, ce;
     epi_chunk_range(*c.g, c.grp, &cb, &ce);
@@ -251,16 +252,20 @@ struct EpiLbs {
       const int e = s * 32 + lane;
       const int rr = e / NCOL, cc = e - rr * NCOL;
       if (cc < n_valid_cols) {
-#pragma unroll
-        for (int rg = 0; rg < 8; ++rg) {
-          const int r = rg * 4 + rr;
-          if (head0 + r < rows) dst[static_cast<size_t>(r) * row_pitch + cc] = stage[r * 25 + cc];
+        float* d = dst + static_cast<size_t>(rr) * row_pitch + cc;
+        const float* sp = stage + rr * 25 + cc;
+#pragma unroll 2
+        for (int rg = 0; rg < 8; ++rg) {               // rows rr, rr+4, ... (incremental addressing: few live registers)
+          if (head0 + rg * 4 + rr < rows) *d = *sp;
+          d += 4 * row_pitch;
+          sp += 100;
         }
       }
     }
     __syncwarp();
   }
 
+  static __device__ __forceinline__ void prefetch(const Params&, EpiCtx&, State&) {}
   static __device__ __forceinline__ void run(const Params& ep, EpiCtx& c, State& st) {
     const int rows = c.g->Wo;
     const int head0 = c.tc.m_tile * kBlockM + c.wq * 32;
@@ -292,17 +297,15 @@ struct EpiLbs {
       {
         const uint32_t t = c.t_acc + static_cast<uint32_t>(colw + pass * 24);
         const bool two = c.g->n_acc == 2;
-        float a[16], b[16];
-        ptx::tmem_ld_32x32b_x16_f(t, a);
-        if (two) ptx::tmem_ld_32x32b_x16_f(t + c.g->block_n, b);
-        ptx::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) x[j] = two ? a[j] + b[j] : a[j];
-        ptx::tmem_ld_32x32b_x8_f(t + 16, a);
-        if (two) ptx::tmem_ld_32x32b_x8_f(t + c.g->block_n + 16, b);
-        ptx::tmem_ld_wait();
+        for (int q = 0; q < 3; ++q) {                                            // 3 x 8 columns: small transient set
+          float a[8], b[8];
+          ptx::tmem_ld_32x32b_x8_f(t + 8 * q, a);
+          if (two) ptx::tmem_ld_32x32b_x8_f(t + c.g->block_n + 8 * q, b);
+          ptx::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 8; ++j) x[16 + j] = two ? a[j] + b[j] : a[j];
+          for (int j = 0; j < 8; ++j) x[8 * q + j] = two ? a[j] + b[j] : a[j];
+        }
       }
       if (pass == 1) epi_release_tmem(c);
 #pragma unroll

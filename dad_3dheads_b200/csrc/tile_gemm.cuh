@@ -35,7 +35,7 @@ constexpr int kMaxPieces = 3;
 constexpr int kMaxMma = 6;
 constexpr int kEpiWarps = 8;
 constexpr int kFirstEpiWarp = 2;
-constexpr int kGemmThreads = (kFirstEpiWarp + kEpiWarps) * 32;   // 320 threads x 192 registers (warp allocation granularity 512) = 61440 <= 64 K
+constexpr int kGemmThreads = (kFirstEpiWarp + kEpiWarps) * 32;   // 320 threads
 constexpr int kTmemCols = 512;
 constexpr int kStageOutBytes = 4096;              // per epilogue warp: 32 rows x 128 B
 constexpr int kGemmSmemLimit = 227 * 1024;
@@ -190,7 +190,8 @@ __device__ __forceinline__ void epi_chunk_range(const GemmGeom& g, int grp, int*
 }
 
 template <class Epi>
-__global__ void __maxnreg__(192)
+// 10 warps = up to 3 warps on one SM sub-partition (16 K registers each) -> at most 168 registers per thread
+__global__ void __launch_bounds__(kGemmThreads, 1)
 tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const typename Epi::Params ep) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle atoms (TMA writes and UMMA reads must agree on the pattern).
@@ -339,6 +340,7 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
       c.bn0 = c.tc.n0 + bin;
       c.tempty = &tempty_bar[acc];
       c.t_acc = tmem_base + (static_cast<uint32_t>(c.wq * 32) << 16) + static_cast<uint32_t>(acc * g.n_acc * g.block_n);
+      Epi::prefetch(ep, c, user_state);            // global reads that do not depend on the accumulator overlap the main loop
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
       ptx::tc_fence_after();
       Epi::run(ep, c, user_state);                 // must call epi_release_tmem(c) exactly once per thread
