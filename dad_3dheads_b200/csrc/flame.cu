@@ -608,17 +608,19 @@ int dad3d_flame_create(dad3d_flame** out, const float* shapedirs_h, const float*
       rh[k] = hb;
       rl[k] = f32_to_f16_bits(x - f16_bits_to_f32(hb));
     }
-    // template: two columns with coefficient 1 (kTmplCol, kTmplCol+1 -- the prep kernel writes 1.0 into both):
-    // column 0 carries hi/lo of scale*T, column 1 the hi/lo of what is left, so the sum is exact in fp32
+    // template: two columns with coefficient 1 (kTmplCol, kTmplCol+1 -- the prep kernel writes 1.0 into both).  The
+    // successive fp16 pieces p0..p3 of scale*T go to (col0.hi, col1.hi, col0.lo, col1.lo): the hi planes alone already
+    // carry 22 bits (what the one-product FAST mode sees), all four planes are exact in fp32.
     float r = v_template_h[n] * h->basis_scale;
-    for (int k = 0; k < 2; ++k) {
-      const unsigned short hb = f32_to_f16_bits(r);
-      r -= f16_bits_to_f32(hb);
-      const unsigned short lb = f32_to_f16_bits(r);
-      r -= f16_bits_to_f32(lb);
-      rh[kTmplCol + k] = hb;
-      rl[kTmplCol + k] = lb;
+    unsigned short pc[4];
+    for (int k = 0; k < 4; ++k) {
+      pc[k] = f32_to_f16_bits(r);
+      r -= f16_bits_to_f32(pc[k]);
     }
+    rh[kTmplCol] = pc[0];
+    rh[kTmplCol + 1] = pc[1];
+    rl[kTmplCol] = pc[2];
+    rl[kTmplCol + 1] = pc[3];
   }
   // (sum of the non-jaw weights, jaw weight) per vertex for the jaw-only fused epilogue
   std::vector<float> w2(static_cast<size_t>(n_vertices) * 2, 0.f);
