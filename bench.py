@@ -34,6 +34,17 @@ FLOPS_PER_IMAGE_ENCODER = 2 * 7_559_801_344        # SURVEY §8(d), analytic
 FLOPS_PER_HEAD_BLEND = 13_140_168                  # 2*15069*(400+36), as written in the reference
 
 
+def _traffic_from_profile():
+    """DRAM bytes per launch of the dominant kernel, from the committed ncu launch list of this same command
+    (profiles/r01_step_summary_*.json, written by tools/summarize_launches.py).  None when no capture is committed."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_step_summary_*.json")))
+    if not files:
+        return None, None
+    d = json.load(open(files[-1]))
+    return d.get("dominant_dram_bytes_per_launch"), os.path.relpath(files[-1], ROOT)
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -226,6 +237,7 @@ def run_ours(args):
         products = {"fp32": 6, "bf16x3": 6, "bf16x2": 3, "bf16": 1}[args.precision]
         achieved = useful_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
         peak = peaks["bf16_tflops_sustained"]
+        traffic, traffic_src = _traffic_from_profile()
         h2d = x_host.numel() * 4
         d2h = sum(v.numel() * v.element_size() for v in host_out.values())
         line = {
@@ -246,7 +258,11 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": {"kernel": "tile_gemm_kernel<EpiConv> (all conv/linear layers, tcgen05)", "bound": "tensor",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                         "traffic": None, "peak_source": peaks["source"] + " bf16 dense, sustained",
+                         "traffic": traffic if B == PER_GPU_BATCH and args.precision == "fp32" else None,
+                         "traffic_unit": "DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, averaged "
+                                         "over the 77 tile-engine launches of one step)", "traffic_source": traffic_src,
+                         "algorithmic_bytes_per_launch": None,
+                         "peak_source": peaks["source"] + " bf16 dense, sustained",
                          "products_per_mac": products, "executed_tflops": achieved * products,
                          "frac_executed": achieved * products / peak if peak else None,
                          "kernel_ms_per_step": gemm_ms / args.steps, "launches_per_step": gemm_launches / args.steps,

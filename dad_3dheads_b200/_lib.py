@@ -12,6 +12,7 @@ DAD3D_ZERO_JAW = 2
 DAD3D_BLEND_FAST = 4
 DAD3D_BLEND_SIMT = 8
 DAD3D_DECODE_UNFUSED = 16
+DAD3D_DECODE_NO_CLUSTER = 32
 
 
 class Dad3dError(RuntimeError):

@@ -391,6 +391,7 @@ int make_plan(dad3d_encoder* enc, int B, void* ws, size_t ws_bytes, bool layout_
     g.stride = s.stride;
     g.R = w->R; g.S = w->S; g.pad_h = s.pad; g.pad_w = s.pad;
     g.cin_blocks = w->cin_pad / kBlockK;
+    g.cl_m = 1; g.cl_n = 1;
     // few row tiles (small maps / small batch): halve the tile width so that twice as many CTAs share the work
     const int m_tiles = g.tiles_w * g.tiles_h * g.tiles_n;
     const bool narrow = w->has_b64 && m_tiles * (w->cout_pad / w->block_n) * 2 <= enc->num_sms;

@@ -490,6 +490,7 @@ struct dad3d_flame {
   float* d_jdirsT = nullptr;                 // [15, 400]
   CUtensorMap map_b[2];                      // box 64 x 128 (unfused path)
   CUtensorMap map_b96[2];                    // box 64 x 96  (fused path)
+  CUtensorMap map_b48[2];                    // box 64 x 48  (fused path, 2x2 clusters: each CTA loads half of a B tile)
   int fused_chunk = 0;                       // heads per pass of the fused path: 4 row tiles per SM
 };
 
@@ -505,9 +506,34 @@ int launch_tile_gemm(const GemmMaps& maps, const GemmGeom& g, const typename Epi
     configured_smem = kGemmSmemLimit;
   }
   const int m_tiles = g.tiles_w * g.tiles_h * g.tiles_n;
-  const int total = g.sched == 1 ? m_tiles : m_tiles * g.n_tiles;
-  const int grid = total < num_sms ? total : num_sms;
-  tile_gemm_kernel<Epi><<<grid, kGemmThreads, smem, stream>>>(maps, g, ep);
+  const int csize = g.cl_m * g.cl_n;
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  cfg.attrs = attr;
+  cfg.numAttrs = 0;
+  if (csize > 1) {
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = csize;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.numAttrs = 1;
+    static int max_clusters = 0;                       // co-resident clusters of this size (GPC packing: < #SM / csize)
+    if (max_clusters == 0) {
+      cfg.gridDim = dim3(num_sms / csize * csize);
+      DAD3D_CUDA_OK(cudaOccupancyMaxActiveClusters(&max_clusters, tile_gemm_kernel<Epi>, &cfg));
+      if (max_clusters < 1) { set_error("no co-resident cluster fits"); return DAD3D_ERR_CUDA; }
+    }
+    const int m_super = ceil_div(m_tiles, g.cl_m);
+    const int clusters = m_super < max_clusters ? m_super : max_clusters;
+    cfg.gridDim = dim3(clusters * csize);
+  } else {
+    const int total = g.sched == 1 ? m_tiles : m_tiles * g.n_tiles;
+    cfg.gridDim = dim3(total < num_sms ? total : num_sms);
+  }
+  DAD3D_CUDA_OK(cudaLaunchKernelEx(&cfg, tile_gemm_kernel<Epi>, maps, g, ep));
   count_launch();
   DAD3D_CUDA_OK(cudaGetLastError());
   return DAD3D_OK;
@@ -675,6 +701,8 @@ int dad3d_flame_create(dad3d_flame** out, const float* shapedirs_h, const float*
     if (!make_tmap_16bit(&h->map_b[p], h->d_basis[p], 2, dims, strides, box, nullptr)) return fail(DAD3D_ERR_CUDA);
     const uint32_t box96[2] = {kBlockK, kFusedBlockN};
     if (!make_tmap_16bit(&h->map_b96[p], h->d_basis[p], 2, dims, strides, box96, nullptr)) return fail(DAD3D_ERR_CUDA);
+    const uint32_t box48[2] = {kBlockK, kFusedBlockN / 2};
+    if (!make_tmap_16bit(&h->map_b48[p], h->d_basis[p], 2, dims, strides, box48, nullptr)) return fail(DAD3D_ERR_CUDA);
   }
   h->fused_chunk = h->num_sms * kBlockM * 4;
   *out = h;
@@ -749,6 +777,8 @@ int dad3d_flame_decode(dad3d_flame* h, const float* params_d, int32_t B, int32_t
       DAD3D_CUDA_OK(cudaGetLastError());
     } else {
       const int block_n = fused ? kFusedBlockN : kBlendBlockN;
+      // big fused passes (>= one row tile per SM): 2x2 thread-block clusters with TMA multicast of both operands
+      const bool clustered = fused && ceil_div(rows, kBlockM) >= h->num_sms && !(flags & DAD3D_DECODE_NO_CLUSTER);
       GemmMaps maps;
       std::memset(&maps, 0, sizeof(maps));
       __half* planes[2] = {a_hi, a_lo};
@@ -756,9 +786,9 @@ int dad3d_flame_decode(dad3d_flame* h, const float* params_d, int32_t B, int32_t
         const uint64_t dims[4] = {static_cast<uint64_t>(kKPad), static_cast<uint64_t>(rows), 1, 1};
         const uint64_t strides[3] = {static_cast<uint64_t>(kKPad) * 2, static_cast<uint64_t>(kKPad) * 2 * rows,
                                      static_cast<uint64_t>(kKPad) * 2 * rows};
-        const uint32_t box[4] = {kBlockK, kBlockM, 1, 1};
+        const uint32_t box[4] = {kBlockK, static_cast<uint32_t>(clustered ? kBlockM / 2 : kBlockM), 1, 1};
         if (!make_tmap_16bit(&maps.a[pi], planes[pi], 4, dims, strides, box, nullptr)) return DAD3D_ERR_CUDA;
-        maps.b[pi] = fused ? h->map_b96[pi] : h->map_b[pi];
+        maps.b[pi] = fused ? (clustered ? h->map_b48[pi] : h->map_b96[pi]) : h->map_b[pi];
       }
       GemmGeom g;
       std::memset(&g, 0, sizeof(g));
@@ -767,6 +797,8 @@ int dad3d_flame_decode(dad3d_flame* h, const float* params_d, int32_t B, int32_t
       g.Wo = rows; g.Ho = 1; g.Nimg = 1;
       g.stride = 1; g.R = 1; g.S = 1; g.pad_h = 0; g.pad_w = 0;
       g.cin_blocks = kKPad / kBlockK;
+      g.cl_m = clustered ? 2 : 1;
+      g.cl_n = clustered ? 2 : 1;
       g.n_tiles = ceil_div(h->n3, block_n);
       g.block_n = block_n;
       g.fmt16 = 0;

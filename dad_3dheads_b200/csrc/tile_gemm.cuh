@@ -57,6 +57,11 @@ struct GemmGeom {
   int mma_acc[kMaxMma];            // which accumulator each product goes to (see "accumulator classes" above)
   int stages;                      // smem ring depth
   unsigned fmt16;                  // 0 = fp16, 1 = bf16
+  int cl_m, cl_n;                  // thread-block cluster of cl_m x cl_n CTAs (1 or 2 each; plain-GEMM geometry and
+                                   // sched 1 only): CTA (ci, cj) of a cluster computes row tile cl_m*Ms+ci, column tile
+                                   // cl_n*Ns+cj; the cl_n CTAs sharing a row tile each load 1/cl_n of the A tile and
+                                   // TMA-multicast it to the others, likewise the cl_m CTAs sharing a column tile for B.
+                                   // Operand traffic from L2 per CTA drops to A/cl_n + B/cl_m.
   int sched;                       // 0: tiles round-robin over CTAs with the column tile fastest (default);
                                    // 1: row-tile persistent -- CTA b owns row tiles b, b+grid, ... and walks ALL column
                                    //    tiles of each (per-row-tile epilogue state is loaded once; all CTAs sweep the
@@ -110,10 +115,21 @@ __device__ __forceinline__ bool tile_at(const GemmGeom& g, int i, TileCoord* tc)
     if (t >= m_tiles * g.n_tiles) return false;
     n = t % g.n_tiles;
     m = t / g.n_tiles;
-  } else {
+  } else if (g.cl_m * g.cl_n == 1) {
     m = static_cast<int>(blockIdx.x) + (i / g.n_tiles) * static_cast<int>(gridDim.x);
     if (m >= m_tiles) return false;
     n = i % g.n_tiles;
+  } else {
+    // clusters walk (row super tile, column super tile) in lock step; tiles past the edge ("ghosts") are still processed
+    // (zero-filled loads, masked stores) so that every CTA of the cluster performs the same number of pipeline steps
+    const int csize = g.cl_m * g.cl_n;
+    const int rank = static_cast<int>(ptx::cluster_ctarank());
+    const int n_super = (g.n_tiles + g.cl_n - 1) / g.cl_n;
+    const int m_super = (m_tiles + g.cl_m - 1) / g.cl_m;
+    const int ms = static_cast<int>(blockIdx.x) / csize + (i / n_super) * (static_cast<int>(gridDim.x) / csize);
+    if (ms >= m_super) return false;
+    m = ms * g.cl_m + rank / g.cl_n;
+    n = (i % n_super) * g.cl_n + rank % g.cl_n;
   }
   *tc = decode_tile(g, m, n);
   return true;
@@ -217,9 +233,10 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
     for (int i = 0; i < g.nB; ++i) ptx::prefetch_tmap(&maps.b[i]);
   }
   if (warp == 1 && lane == 0) {
+    const int n_peers = g.cl_m + g.cl_n - 1;       // CTAs that read what I multicast == CTAs that multicast to me
     for (int s = 0; s < g.stages; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
-      ptx::mbar_init(&empty_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], n_peers);     // a slot is free when every consumer of my slices has released it
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(&tfull_bar[b], 1);
@@ -235,6 +252,15 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // ---- cluster bookkeeping (csize == 1: everything below degenerates to the single-CTA protocol)
+  const int csize = g.cl_m * g.cl_n;
+  const int crank = csize > 1 ? static_cast<int>(ptx::cluster_ctarank()) : 0;
+  const int ci = crank / g.cl_n, cj = crank % g.cl_n;
+  uint16_t mask_a = 0, mask_b = 0;                 // CTAs sharing my row tile (A) / my column tile (B)
+  for (int j = 0; j < g.cl_n; ++j) mask_a |= static_cast<uint16_t>(1u << (ci * g.cl_n + j));
+  for (int i = 0; i < g.cl_m; ++i) mask_b |= static_cast<uint16_t>(1u << (i * g.cl_n + cj));
+  const uint16_t mask_peers = mask_a | mask_b;     // everyone I exchange operand slices with (including myself)
+  if (csize > 1) ptx::cluster_sync_all();          // peers' barriers are initialised before anyone signals them
   // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) may overlap the previous kernel's tail;
   // nothing below may touch global memory before the previous grid has fully completed.
   ptx::grid_dep_launch();
@@ -258,13 +284,24 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
           uint8_t* st = smem + stage * stage_bytes;
           const int cw = tc.w0 * g.stride + s - g.pad_w;
           const int ch = tc.h0 * g.stride + r - g.pad_h;
-          for (int i = 0; i < g.nA; ++i)
-            ptx::tma_load_4d(st + i * kTileABytes, &maps.a[i], &full_bar[stage], cb * kBlockK, cw, ch, tc.n0);
           uint8_t* sb = st + g.nA * kTileABytes;
           const int kcol = kb * kBlockK;
-          for (int i = 0; i < g.nB; ++i)
-            ptx::tma_load_2d(sb + i * g.block_n * kBlockK * 2, &maps.b[i], &full_bar[stage], kcol,
-                             tc.n_tile * g.block_n);
+          if (csize == 1) {
+            for (int i = 0; i < g.nA; ++i)
+              ptx::tma_load_4d(st + i * kTileABytes, &maps.a[i], &full_bar[stage], cb * kBlockK, cw, ch, tc.n0);
+            for (int i = 0; i < g.nB; ++i)
+              ptx::tma_load_2d(sb + i * g.block_n * kBlockK * 2, &maps.b[i], &full_bar[stage], kcol,
+                               tc.n_tile * g.block_n);
+          } else {
+            // my 1/cl_n slice of the A rows and 1/cl_m slice of the B rows, multicast to the CTAs that share them
+            const int a_rows = kBlockM / g.cl_n, b_rows = g.block_n / g.cl_m;
+            for (int i = 0; i < g.nA; ++i)
+              ptx::tma_load_4d_mc(st + i * kTileABytes + cj * a_rows * kBlockK * 2, &maps.a[i], &full_bar[stage],
+                                  cb * kBlockK, cw + cj * a_rows, ch, tc.n0, mask_a);
+            for (int i = 0; i < g.nB; ++i)
+              ptx::tma_load_2d_mc(sb + i * g.block_n * kBlockK * 2 + ci * b_rows * kBlockK * 2, &maps.b[i],
+                                  &full_bar[stage], kcol, tc.n_tile * g.block_n + ci * b_rows, mask_b);
+          }
           if (++stage == g.stages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -300,7 +337,8 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
               started |= 1u << a_id;
             }
           }
-          ptx::umma_commit(&empty_bar[stage]);   // smem slot reusable once these MMAs have read it
+          if (csize == 1) ptx::umma_commit(&empty_bar[stage]);   // smem slot reusable once these MMAs have read it
+          else ptx::umma_commit_mc(&empty_bar[stage], mask_peers);   // ... tell every CTA that fills this slot
           if (++stage == g.stages) { stage = 0; phase ^= 1u; }
         }
         ptx::umma_commit(&tfull_bar[acc]);        // accumulator complete
@@ -353,6 +391,7 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (csize > 1) ptx::cluster_sync_all();          // nobody leaves while a peer may still write my smem / barriers
   if (warp == 0) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, kTmemCols);

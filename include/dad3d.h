@@ -34,6 +34,8 @@ typedef struct dad3d_encoder dad3d_encoder;
 #define DAD3D_ERR_CUDA (-2)
 #define DAD3D_ERR_UNSUPPORTED (-3)
 
+#define DAD3D_DECODE_NO_CLUSTER 32 /* A/B aid: fused decode without thread-block clusters / TMA multicast */
+
 /* Widths of the fields of the 3DMM parameter vector, sliced in the reference's hard-coded order
  * shape, expression, jaw, rotation, eyeballs, neck, translation, scale
  * (model_training/model/flame.py:41-84 FlameParams.from_3dmm; dad_3dnet.yaml:5-12 gives 300/100/3/6/0/0/3/1 = 413). */
