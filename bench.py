@@ -213,11 +213,19 @@ def run_ours(args):
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()                                 # sampled under load: warm-up + timed region (same kernels)
+    n_warm = max(args.warmup, 3)
     t_w = time.perf_counter()
-    n_w = 0
-    while n_w < max(args.warmup, 3) or time.perf_counter() - t_w < 1.0:    # >= W steps and >= 1 s so clocks settle
+    for _ in range(n_warm):
         step_device()
-        n_w += 1
+    torch.cuda.synchronize()
+    # keep the GPU under the same load for >= 1 s before timing so the sampled clocks have settled; the number of extra
+    # steps is decided on rank 0 and broadcast (every step contains collectives, so all ranks must run the same count)
+    per_step = max((time.perf_counter() - t_w) / n_warm, 1e-4)
+    extra = torch.tensor([max(0, int((1.0 - (time.perf_counter() - t_w)) / per_step) + 1)], device=dev)
+    if distributed:
+        dist.broadcast(extra, 0)
+    for _ in range(int(extra.item())):
+        step_device()
     torch.cuda.synchronize()
     launches0 = _lib.launch_count()
     ms_total, prof = timed(step_device, args.steps, profile=True)
