@@ -12,7 +12,7 @@ DAD3D_ZERO_JAW = 2
 DAD3D_BLEND_FAST = 4
 DAD3D_BLEND_SIMT = 8
 DAD3D_DECODE_UNFUSED = 16
-DAD3D_DECODE_NO_CLUSTER = 32
+DAD3D_DECODE_CLUSTER = 32
 
 
 class Dad3dError(RuntimeError):
@@ -50,6 +50,8 @@ SIGNATURES = {
     "dad3d_encoder_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int32]),
     "dad3d_encoder_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_size_t, C.c_void_p]),
+    "dad3d_preprocess": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p]),
     "dad3d_encoder_set_profile": (C.c_int, [C.c_void_p, C.c_int32]),
     "dad3d_encoder_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong),
                                               C.POINTER(C.c_double)]),

@@ -134,33 +134,51 @@ struct EpiConv {
     const int swz = (c.lane >> 1) & 3;
     const uint8_t* rowp = c.stage + c.lane * 64;
     const int col = c.col0 + first_col(c, H);
+    // 1) every global load of this half (up to 3 planes x 4 row-segment sweeps) is issued before anything waits on one:
+    //    a single memory round trip instead of one per plane
+    uint4 q[3][4];
+    const int planes = ep.res.planes;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int idx = it * 32 + c.lane;
+      const int row = idx >> 2, seg = idx & 3;
+      const long long spix = __shfl_sync(0xffffffffu, c.pix, row);
+      const int svalid = __shfl_sync(0xffffffffu, c.valid ? 1 : 0, row);
+      const uint16_t* src = ep.res.base + spix * ep.res.C + col + seg * 8;
+#pragma unroll
+      for (int p = 0; p < 3; ++p) {
+        q[p][it] = make_uint4(0, 0, 0, 0);
+        if (p < planes && svalid) q[p][it] = __ldg(reinterpret_cast<const uint4*>(src + p * ep.res.plane));
+      }
+    }
     if (c.lane == 0) ptx::bulk_wait_read0();          // an earlier TMA store may still be reading the staging tile
     __syncwarp();
 #pragma unroll
     for (int j = 0; j < 32; ++j) st.r[H * 32 + j] = 0.f;
-    for (int p = ep.res.planes - 1; p >= 0; --p) {
+    // 2) transpose plane by plane through the staging tile (smallest piece first) and sum this lane's row
 #pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        const int idx = it * 32 + c.lane;
-        const int row = idx >> 2, seg = idx & 3;
-        const long long spix = __shfl_sync(0xffffffffu, c.pix, row);
-        const int svalid = __shfl_sync(0xffffffffu, c.valid ? 1 : 0, row);
-        uint4 q = make_uint4(0, 0, 0, 0);
-        if (svalid) q = __ldg(reinterpret_cast<const uint4*>(ep.res.base + p * ep.res.plane + spix * ep.res.C + col + seg * 8));
-        *reinterpret_cast<uint4*>(c.stage + row * 64 + ((seg ^ ((row >> 1) & 3)) << 4)) = q;
-      }
-      __syncwarp();
+    for (int pp = 0; pp < 3; ++pp) {
+      const int p = 2 - pp;
+      if (p < planes) {
 #pragma unroll
-      for (int q4 = 0; q4 < 4; ++q4) {
-        const uint4 q = *reinterpret_cast<const uint4*>(rowp + ((q4 ^ swz) << 4));
-        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          st.r[H * 32 + 8 * q4 + 2 * j] += __uint_as_float(w[j] << 16);
-          st.r[H * 32 + 8 * q4 + 2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+        for (int it = 0; it < 4; ++it) {
+          const int idx = it * 32 + c.lane;
+          const int row = idx >> 2, seg = idx & 3;
+          *reinterpret_cast<uint4*>(c.stage + row * 64 + ((seg ^ ((row >> 1) & 3)) << 4)) = q[p][it];
         }
+        __syncwarp();
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const uint4 v = *reinterpret_cast<const uint4*>(rowp + ((q4 ^ swz) << 4));
+          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            st.r[H * 32 + 8 * q4 + 2 * j] += __uint_as_float(w[j] << 16);
+            st.r[H * 32 + 8 * q4 + 2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+          }
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
   }
 

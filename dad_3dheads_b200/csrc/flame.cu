@@ -238,6 +238,7 @@ struct EpiLbs {
     float R[12];             // rest transform  [R | t] rows (rotation pre-divided by the basis scale)
     float Jw[12];            // jaw transform
     float cx, cy, cz, sc, tx, ty;
+    float wl;                // this lane's entry of the tile's (w_rest, w_jaw) table: lane 2i / 2i+1 <-> vertex i
   };
 
   // write the warp's staged [32 rows][NCOL floats] (row pitch 25) as contiguous runs of NCOL floats per head row:
@@ -254,7 +255,7 @@ struct EpiLbs {
       if (cc < n_valid_cols) {
         float* d = dst + static_cast<size_t>(rr) * row_pitch + cc;
         const float* sp = stage + rr * 25 + cc;
-#pragma unroll 2
+#pragma unroll 4
         for (int rg = 0; rg < 8; ++rg) {               // rows rr, rr+4, ... (incremental addressing: few live registers)
           if (head0 + rg * 4 + rr < rows) *d = *sp;
           d += 4 * row_pitch;
@@ -265,14 +266,13 @@ struct EpiLbs {
     __syncwarp();
   }
 
-  static __device__ __forceinline__ void prefetch(const Params&, EpiCtx&, State&) {}
-  static __device__ __forceinline__ void run(const Params& ep, EpiCtx& c, State& st) {
-    const int rows = c.g->Wo;
-    const int head0 = c.tc.m_tile * kBlockM + c.wq * 32;
-    float* stage = reinterpret_cast<float*>(c.stage);
-
+  // everything that does not depend on the accumulator is fetched while the tile's MMAs still run
+  static __device__ __forceinline__ void prefetch(const Params& ep, EpiCtx& c, State& st) {
+    const int vb = (c.col0 + c.grp * 48) / 3;                                    // first vertex of this warp
+    st.wl = (vb * 2 + c.lane < ep.nv * 2) ? __ldg(&ep.w2[vb * 2 + c.lane]) : 0.f;
     if (c.tc.m_tile != c.prev_m_tile) {            // per-head transforms -> registers, once per row tile
-      const int h = min(head0 + c.lane, rows - 1);
+      const int head0 = c.tc.m_tile * kBlockM + c.wq * 32;
+      const int h = min(head0 + c.lane, c.g->Wo - 1);
       const float4* src = reinterpret_cast<const float4*>(ep.xf + static_cast<size_t>(h) * kXfFloats);
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
@@ -285,26 +285,32 @@ struct EpiLbs {
       const float4 w = __ldg(&src[16]);
       st.cx = u.x; st.cy = u.y; st.cz = u.z; st.sc = u.w; st.tx = w.x; st.ty = w.y;
     }
+  }
+  static __device__ __forceinline__ void run(const Params& ep, EpiCtx& c, State& st) {
+    const int rows = c.g->Wo;
+    const int head0 = c.tc.m_tile * kBlockM + c.wq * 32;
+    float* stage = reinterpret_cast<float*>(c.stage);
 
     const int colw = c.grp * 48;
     const int vb = (c.col0 + colw) / 3;                                          // first vertex of this warp
-    // (w_rest, w_jaw) of the warp's 16 vertices: one coalesced load, broadcast by shuffles
-    const float wl = (vb * 2 + c.lane < ep.nv * 2) ? __ldg(&ep.w2[vb * 2 + c.lane]) : 0.f;
+    const float wl = st.wl;
 
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
       float x[24];                                                               // 8 vertices of this pass
       {
         const uint32_t t = c.t_acc + static_cast<uint32_t>(colw + pass * 24);
-        const bool two = c.g->n_acc == 2;
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {                                            // 3 x 8 columns: small transient set
-          float a[8], b[8];
-          ptx::tmem_ld_32x32b_x8_f(t + 8 * q, a);
-          if (two) ptx::tmem_ld_32x32b_x8_f(t + c.g->block_n + 8 * q, b);
+        ptx::tmem_ld_32x32b_x16_f(t, x);
+        ptx::tmem_ld_32x32b_x8_f(t + 16, x + 16);
+        if (c.g->n_acc == 2) {                                                   // all four loads in flight, one wait
+          float b[24];
+          ptx::tmem_ld_32x32b_x16_f(t + c.g->block_n, b);
+          ptx::tmem_ld_32x32b_x8_f(t + c.g->block_n + 16, b + 16);
           ptx::tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 8; ++j) x[8 * q + j] = two ? a[j] + b[j] : a[j];
+          for (int j = 0; j < 24; ++j) x[j] += b[j];
+        } else {
+          ptx::tmem_ld_wait();
         }
       }
       if (pass == 1) epi_release_tmem(c);
@@ -778,7 +784,9 @@ int dad3d_flame_decode(dad3d_flame* h, const float* params_d, int32_t B, int32_t
     } else {
       const int block_n = fused ? kFusedBlockN : kBlendBlockN;
       // big fused passes (>= one row tile per SM): 2x2 thread-block clusters with TMA multicast of both operands
-      const bool clustered = fused && ceil_div(rows, kBlockM) >= h->num_sms && !(flags & DAD3D_DECODE_NO_CLUSTER);
+      // Measured on B200 (profiles/README.md): with 4-CTA clusters L2 sector reads drop only 28 % and the pass gets 17 %
+      // slower (132 of 148 SMs usable, cross-CTA barrier coupling), so clusters are opt-in.
+      const bool clustered = fused && ceil_div(rows, kBlockM) >= h->num_sms && (flags & DAD3D_DECODE_CLUSTER);
       GemmMaps maps;
       std::memset(&maps, 0, sizeof(maps));
       __half* planes[2] = {a_hi, a_lo};

@@ -140,7 +140,7 @@ class FlameDecoder:
 
     def decode(self, params: Tensor, *, want_vertices: bool = True, want_projected: bool = False, to_2d: bool = True,
                zero_rot: bool = False, zero_jaw: bool = False, image_size: float = 256.0, fast: bool = False,
-               simt: bool = False, unfused: bool = False, no_cluster: bool = False):
+               simt: bool = False, unfused: bool = False, cluster: bool = False):
         """params: [B, num_params] fp32 CUDA tensor on this decoder's device.  Returns (vertices3d|None, projected|None)."""
         assert params.is_cuda and params.dtype == torch.float32 and params.ndim == 2
         assert params.shape[1] == self.num_params, (params.shape, self.num_params)
@@ -153,7 +153,7 @@ class FlameDecoder:
             return v3, pj
         flags = ((_lib.DAD3D_ZERO_ROT if zero_rot else 0) | (_lib.DAD3D_ZERO_JAW if zero_jaw else 0) |
                  (_lib.DAD3D_BLEND_FAST if fast else 0) | (_lib.DAD3D_BLEND_SIMT if simt else 0) |
-                 (_lib.DAD3D_DECODE_UNFUSED if unfused else 0) | (_lib.DAD3D_DECODE_NO_CLUSTER if no_cluster else 0))
+                 (_lib.DAD3D_DECODE_UNFUSED if unfused else 0) | (_lib.DAD3D_DECODE_CLUSTER if cluster else 0))
         nbytes = int(self.lib.dad3d_flame_workspace_bytes(self._h, B))
         ws = self._ws.get(params.device, nbytes)
         stream = torch.cuda.current_stream(params.device).cuda_stream

@@ -200,6 +200,32 @@ class FaceMeshPredictor:
         config = load_yaml(cfg_path) if os.path.isfile(cfg_path) else dict(DEFAULT_CONFIG)
         return cls(config=config, cuda_id=cuda_id, state_dict=state_dict, precision=precision)
 
+    # ------------------------------------------------------------------ device-side pre-processing
+    def preprocess_batch(self, images) -> Tensor:
+        """images: list of HxWx3 uint8 RGB arrays/tensors (any sizes).  -> [B,3,S,S] fp32 on the GPU, bit-identical to
+        ``_transform`` (cv2 INTER_LINEAR letter-box + constant-0 pad + imagenet normalisation); only the raw uint8
+        pixels cross the PCIe bus."""
+        import ctypes as C
+        lib = _lib.load()
+        S = self._img_size
+        out = torch.empty(len(images), 3, S, S, dtype=torch.float32, device=self.device)
+        mean = (np.array(_MEAN, dtype=np.float32) * 255.0).astype(np.float32)
+        inv = np.reciprocal(np.array(_STD, dtype=np.float32) * 255.0, dtype=np.float32)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        keep = []
+        with torch.cuda.device(self.device):
+            for i, im in enumerate(images):
+                t = torch.as_tensor(im)
+                assert t.dtype == torch.uint8 and t.ndim == 3 and t.shape[2] == 3
+                h, w = int(t.shape[0]), int(t.shape[1])
+                scale = S / float(max(h, w))
+                nh, nw = (py3round(h * scale), py3round(w * scale)) if scale != 1.0 else (h, w)
+                d = t.contiguous().to(self.device, non_blocking=True)
+                keep.append(d)
+                _lib.check(lib.dad3d_preprocess(d.data_ptr(), h, w, nh, nw, S, mean.ctypes.data, inv.ctypes.data,
+                                                out[i].data_ptr(), stream), "dad3d_preprocess")
+        return out
+
     # ------------------------------------------------------------------ batched device-resident API (new)
     def _landmark_index(self, subset: str) -> Tensor:
         if self._static is None:

@@ -34,7 +34,8 @@ typedef struct dad3d_encoder dad3d_encoder;
 #define DAD3D_ERR_CUDA (-2)
 #define DAD3D_ERR_UNSUPPORTED (-3)
 
-#define DAD3D_DECODE_NO_CLUSTER 32 /* A/B aid: fused decode without thread-block clusters / TMA multicast */
+#define DAD3D_DECODE_CLUSTER 32 /* A/B aid: fused decode as 2x2 thread-block clusters with TMA multicast of both operands
+                                  (measured slower on B200, so off by default) */
 
 /* Widths of the fields of the 3DMM parameter vector, sliced in the reference's hard-coded order
  * shape, expression, jaw, rotation, eyeballs, neck, translation, scale
@@ -127,6 +128,16 @@ DAD3D_API size_t dad3d_encoder_workspace_bytes(dad3d_encoder* enc, int32_t B);
 DAD3D_API int dad3d_encoder_forward(dad3d_encoder* enc, const float* images_d, int32_t B, float* params_d,
                                     float* landmarks_d, float* heatmap_d, void* workspace_d, size_t workspace_bytes,
                                     dad3d_stream stream);
+
+/* ---- device-side pre-processing (SURVEY §8f "next" row 2) --------------------------------------------------------------
+ * dad3d_preprocess replaces FaceMeshPredictor._transform + _array_to_batch (predictor.py:85-89,195-203: albumentations
+ *   LongestMaxSize -> PadIfNeeded -> Normalize -> HWC->CHW) for one image: image_d [H,W,3] uint8 RGB (device) ->
+ *   out_d [3,img_size,img_size] fp32.  new_h/new_w are the letter-boxed sizes (py3round(dim * img_size / max(H,W)),
+ *   computed by the caller exactly as predictor.py:117-123 does); the 8-bit bilinear resize is bit-exact with
+ *   cv2.resize(INTER_LINEAR).  mean255_h / inv_std255_h: the three fp32 constants mean*255 and 1/(std*255). */
+DAD3D_API int dad3d_preprocess(const uint8_t* image_d, int32_t H, int32_t W, int32_t new_h, int32_t new_w,
+                               int32_t img_size, const float* mean255_h, const float* inv_std255_h, float* out_d,
+                               dad3d_stream stream);
 
 /* Live timing of the dominant kernel (the tcgen05 tile engine) for bench.py's roofline: while on, every conv / linear
  * launch is bracketed by CUDA events on the launching stream.  profile_read synchronises those events and returns their

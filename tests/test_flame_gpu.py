@@ -148,10 +148,10 @@ def test_chunk_boundary_and_batch_independence(head_mesh, cuda_device):
     v_sel, pj_sel = dec.decode(p[sel], want_vertices=True, want_projected=True)
     assert torch.equal(v3[sel], v_sel) and torch.equal(pj[sel], pj_sel)
     assert torch.isfinite(v3).all()
-    # the big passes run as 2x2 thread-block clusters with TMA multicast; same arithmetic without clusters
+    # opt-in variant: big passes as 2x2 thread-block clusters with TMA multicast of both operands -- same arithmetic
     n = props.multi_processor_count * 128 + 77
     va, pa = dec.decode(p[:n], want_vertices=True, want_projected=True)
-    vb, pb = dec.decode(p[:n], want_vertices=True, want_projected=True, no_cluster=True)
+    vb, pb = dec.decode(p[:n], want_vertices=True, want_projected=True, cluster=True)
     assert torch.equal(va, vb) and torch.equal(pa, pb)
 
 
