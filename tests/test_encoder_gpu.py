@@ -109,3 +109,16 @@ def test_batch_64_matches_oracle_subset(sd, cuda_device):
         ref = flame_regression_forward(x[sel].double(), {k: v.double() for k, v in sd.items()})
     assert _rel(p[sel], ref[OUTPUT_3DMM_PARAMS]) < 3e-5 and _rel(l[sel], ref[OUTPUT_2D_LANDMARKS]) < 3e-5
     assert torch.isfinite(p).all()
+
+
+def test_encoder_golden_fixture(sd, cuda_device):
+    """tests/golden/encoder_golden.npz (tools/make_golden.py: fp64 oracle, weight seed 0, image seed 777)."""
+    import os
+    import numpy as np
+    from dad_3dheads_b200.encoder import Dad3dEncoder
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "encoder_golden.npz"))
+    x = torch.randn(2, 3, 256, 256, generator=torch.Generator().manual_seed(int(z["image_seed"])))
+    out = Dad3dEncoder(sd, cuda_device, precision="fp32")(x.to(cuda_device))
+    assert _rel(out[OUTPUT_3DMM_PARAMS], torch.from_numpy(z["params"])) < 3e-5
+    assert _rel(out[OUTPUT_2D_LANDMARKS], torch.from_numpy(z["landmarks"])) < 3e-5
+    assert _rel(out[OUTPUT_LANDMARKS_HEATMAP].sum(dim=(2, 3)), torch.from_numpy(z["heatmap_checksum"])) < 3e-5

@@ -27,5 +27,22 @@ def main():
     print("wrote", out, os.path.getsize(out))
 
 
+def encoder_golden():
+    """Encoder golden: seed-0 synthetic weights, 2 seeded images -> params / landmarks from the fp64 oracle."""
+    from dad_3dheads_b200.encoder_weights import synthetic_state_dict
+    from oracle.encoder_oracle import (OUTPUT_2D_LANDMARKS, OUTPUT_3DMM_PARAMS, OUTPUT_LANDMARKS_HEATMAP,
+                                       flame_regression_forward)
+    sd = {k: v.double() for k, v in synthetic_state_dict(0).items()}
+    x = torch.randn(2, 3, 256, 256, generator=torch.Generator().manual_seed(777))
+    with torch.no_grad():
+        out = flame_regression_forward(x.double(), sd)
+    path = os.path.join(ROOT, "tests", "golden", "encoder_golden.npz")
+    np.savez_compressed(path, image_seed=np.int64(777), weight_seed=np.int64(0),
+                        params=out[OUTPUT_3DMM_PARAMS].float().numpy(), landmarks=out[OUTPUT_2D_LANDMARKS].float().numpy(),
+                        heatmap_checksum=out[OUTPUT_LANDMARKS_HEATMAP].sum(dim=(2, 3)).float().numpy())
+    print("wrote", path, os.path.getsize(path))
+
+
 if __name__ == "__main__":
     main()
+    encoder_golden()
