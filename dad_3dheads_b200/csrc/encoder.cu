@@ -37,6 +37,7 @@ struct ConvW {
   CUtensorMap map_b[kMaxPieces];      // box 64 x block_n
   CUtensorMap map_b64[kMaxPieces];    // box 64 x 64 (small problems: more, narrower tiles to fill the SMs)
   bool has_b64 = false;
+  bool has_identity = false;          // identity columns appended after the conv's K columns (residual-as-K-extension)
 };
 
 int pick_block_n(int cout) {
@@ -392,6 +393,7 @@ int make_plan(dad3d_encoder* enc, int B, void* ws, size_t ws_bytes, bool layout_
     g.R = w->R; g.S = w->S; g.pad_h = s.pad; g.pad_w = s.pad;
     g.cin_blocks = w->cin_pad / kBlockK;
     g.cl_m = 1; g.cl_n = 1;
+    const bool res_in_k = s.res >= 0 && s.res_mode == 1 && w->has_identity;
     // few row tiles (small maps / small batch): halve the tile width so that twice as many CTAs share the work
     const int m_tiles = g.tiles_w * g.tiles_h * g.tiles_n;
     const bool narrow = w->has_b64 && m_tiles * (w->cout_pad / w->block_n) * 2 <= enc->num_sms;
@@ -403,6 +405,14 @@ int make_plan(dad3d_encoder* enc, int B, void* ws, size_t ws_bytes, bool layout_
     g.n_acc = enc->n_acc;
     for (int i = 0; i < enc->n_mma; ++i) { g.mma_a[i] = enc->mma_a[i]; g.mma_b[i] = enc->mma_b[i]; g.mma_acc[i] = enc->mma_acc[i]; }
     g.fmt16 = 1;
+    if (res_in_k) {                                   // "+ identity(x)" performed by the tensor core
+      g.res_kb = block_n / kBlockK;
+      g.n_mma_res = enc->P;
+      for (int i = 0; i < enc->P; ++i) {
+        g.mma_res_a[i] = enc->P - 1 - i;              // smallest piece first
+        g.mma_res_acc[i] = (enc->n_acc == 2 && g.mma_res_a[i] != 0) ? 1 : 0;
+      }
+    }
     g.stages = gemm_max_stages(g);
     if (g.stages < 2) { set_error("layer " + w->name + ": pipeline does not fit shared memory"); return DAD3D_ERR_INVALID; }
     for (int p = 0; p < enc->P; ++p) {
@@ -417,11 +427,23 @@ int make_plan(dad3d_encoder* enc, int B, void* ws, size_t ws_bytes, bool layout_
       if (!make_tmap_16bit(&s.maps.a[p], basep, 4, dims, strides, box, es)) return DAD3D_ERR_CUDA;
       s.maps.b[p] = narrow ? w->map_b64[p] : w->map_b[p];
     }
+    if (res_in_k) {
+      const TensorInfo& tr = plan->tensors[s.res];
+      for (int p = 0; p < enc->P; ++p) {
+        const uint64_t dims[4] = {static_cast<uint64_t>(tr.C), static_cast<uint64_t>(tr.W), static_cast<uint64_t>(tr.H),
+                                  static_cast<uint64_t>(tr.N)};
+        const uint64_t strides[3] = {static_cast<uint64_t>(tr.C) * 2, static_cast<uint64_t>(tr.W) * tr.C * 2,
+                                     static_cast<uint64_t>(tr.H) * tr.W * tr.C * 2};
+        const uint32_t box[4] = {kBlockK, static_cast<uint32_t>(g.tw), static_cast<uint32_t>(g.th), static_cast<uint32_t>(g.tn)};
+        const uint16_t* basep = reinterpret_cast<const uint16_t*>(tr.ptr) + static_cast<size_t>(p) * tr.plane_elems();
+        if (!make_tmap_16bit(&s.maps.r[p], basep, 4, dims, strides, box, nullptr)) return DAD3D_ERR_CUDA;
+      }
+    }
     EpiConv::Params& ep = s.epi;
     std::memset(&ep, 0, sizeof(ep));
     ep.bias = w->d_bias;
     ep.relu = s.relu;
-    ep.res_mode = s.res_mode;
+    ep.res_mode = res_in_k ? 0 : s.res_mode;
     ep.res = view(s.res);
     if (s.res >= 0 && plan->tensors[s.res].C != w->cout_pad) {
       set_error("layer " + w->name + ": residual channel mismatch");
@@ -580,9 +602,14 @@ int dad3d_encoder_create(dad3d_encoder** out, const dad3d_conv_weights* layers, 
     cw.block_n = pick_block_n(L.cout);
     cw.cout_pad = ceil_div(L.cout, cw.block_n) * cw.block_n;
     cw.cin_pad = ceil_div(L.cin, kBlockK) * kBlockK;
-    const size_t ktot = static_cast<size_t>(L.R) * L.S * cw.cin_pad;
+    // the last 1x1 of a ResUnit ("...c3") gets identity columns appended to its K axis: [W | I] * [a ; residual]
+    cw.has_identity = name.size() > 2 && name.compare(name.size() - 2, 2, "c3") == 0 && L.R == 1 && L.S == 1;
+    const size_t ktot_main = static_cast<size_t>(L.R) * L.S * cw.cin_pad;
+    const size_t ktot = ktot_main + (cw.has_identity ? cw.cout_pad : 0);
     const size_t plane = static_cast<size_t>(cw.cout_pad) * ktot;
     std::vector<uint16_t> packed(plane * pieces, 0);
+    if (cw.has_identity)
+      for (int o = 0; o < cw.cout_pad; ++o) packed[static_cast<size_t>(o) * ktot + ktot_main + o] = 0x3F80;   // bf16 1.0, piece 0
     for (int o = 0; o < L.cout; ++o)
       for (int t = 0; t < L.R * L.S; ++t)
         for (int c = 0; c < L.cin; ++c) {

@@ -55,6 +55,13 @@ struct GemmGeom {
   int mma_a[kMaxMma], mma_b[kMaxMma];
   int n_acc;                       // 1 or 2 TMEM accumulators per tile (2 * n_acc * block_n <= 512 columns)
   int mma_acc[kMaxMma];            // which accumulator each product goes to (see "accumulator classes" above)
+  int res_kb;                      // residual-as-K-extension: after the conv's k-blocks, block_n/64 more k-blocks whose A
+                                   // tiles come from the residual tensor (maps.r, at the OUTPUT pixel coordinates, the
+                                   // tile's own channel range) and whose B tiles are the identity columns appended to the
+                                   // packed weights -- the tensor core performs "+ identity(x)" and the residual rides the
+                                   // TMA pipeline (deep prefetch, no epilogue loads).  0 = off.
+  int n_mma_res;                   // products issued for a residual k-block: (mma_res_a[i], B piece 0) -> mma_res_acc[i]
+  int mma_res_a[kMaxPieces], mma_res_acc[kMaxPieces];
   int stages;                      // smem ring depth
   unsigned fmt16;                  // 0 = fp16, 1 = bf16
   int cl_m, cl_n;                  // thread-block cluster of cl_m x cl_n CTAs (1 or 2 each; plain-GEMM geometry and
@@ -71,7 +78,8 @@ struct GemmGeom {
 struct GemmMaps {
   CUtensorMap a[kMaxPieces];       // rank-4 (C, W, H, N), box (64, tw*stride, th*stride, tn), swizzle 128B
   CUtensorMap b[kMaxPieces];       // rank-2 (Ktot, Cout_pad), box (64, block_n), swizzle 128B
-  CUtensorMap c[kMaxPieces];       // output planes, rank-4 (C, Wo, Ho, N), box (block_n/2, 32-pixel sub-box), for TMA stores
+  CUtensorMap c[kMaxPieces];       // output planes, rank-4 (C, Wo, Ho, N), box (32 ch, 32-pixel sub-box), for TMA stores
+  CUtensorMap r[kMaxPieces];       // residual planes, rank-4 (C, Wo, Ho, N), box (64, tw, th, tn)  (res_kb > 0)
 };
 
 __host__ __device__ inline int gemm_stage_bytes(const GemmGeom& g) {
@@ -274,7 +282,20 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
       const uint32_t tx_bytes = static_cast<uint32_t>(stage_bytes);
       TileCoord tc;
       for (int ti = 0; tile_at(g, ti, &tc); ++ti) {
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = 0; kb < num_kb + g.res_kb; ++kb) {
+          if (kb >= num_kb) {                      // residual k-block: A = residual tile, B = identity columns
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+            // only B piece 0 carries the identity (the other planes are zero there and are never multiplied)
+            ptx::mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(g.nA * kTileABytes + g.block_n * kBlockK * 2));
+            uint8_t* st = smem + stage * stage_bytes;
+            const int rc = tc.n_tile * g.block_n + (kb - num_kb) * kBlockK;
+            for (int i = 0; i < g.nA; ++i)
+              ptx::tma_load_4d(st + i * kTileABytes, &maps.r[i], &full_bar[stage], rc, tc.w0, tc.h0, tc.n0);
+            ptx::tma_load_2d(st + g.nA * kTileABytes, &maps.b[0], &full_bar[stage], num_kb * kBlockK + rc,
+                             tc.n_tile * g.block_n);
+            if (++stage == g.stages) { stage = 0; phase ^= 1u; }
+            continue;
+          }
           const int tap = kb / g.cin_blocks;
           const int cb = kb - tap * g.cin_blocks;
           const int r = tap / g.S;
@@ -320,15 +341,19 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * g.n_acc * g.block_n);
         uint32_t started = 0;                        // bit a set once accumulator a has received its first MMA
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = 0; kb < num_kb + g.res_kb; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
           const uint32_t sa = ptx::smem_u32(smem + stage * stage_bytes);
           const uint32_t sb = sa + g.nA * kTileABytes;
-          for (int i = 0; i < g.n_mma; ++i) {
-            const uint64_t adesc = ptx::make_kmajor_sw128_desc(sa + g.mma_a[i] * kTileABytes);
-            const uint64_t bdesc = ptx::make_kmajor_sw128_desc(sb + g.mma_b[i] * g.block_n * kBlockK * 2);
-            const uint32_t a_id = static_cast<uint32_t>(g.mma_acc[i]);
+          const bool res_block = kb >= num_kb;
+          const int n_prod = res_block ? g.n_mma_res : g.n_mma;
+          for (int i = 0; i < n_prod; ++i) {
+            const int pa = res_block ? g.mma_res_a[i] : g.mma_a[i];
+            const int pb = res_block ? 0 : g.mma_b[i];
+            const uint64_t adesc = ptx::make_kmajor_sw128_desc(sa + pa * kTileABytes);
+            const uint64_t bdesc = ptx::make_kmajor_sw128_desc(sb + pb * g.block_n * kBlockK * 2);
+            const uint32_t a_id = static_cast<uint32_t>(res_block ? g.mma_res_acc[i] : g.mma_acc[i]);
             const uint32_t d_acc = d_tmem + a_id * static_cast<uint32_t>(g.block_n);
 #pragma unroll
             for (int k = 0; k < kBlockK / 16; ++k) {
