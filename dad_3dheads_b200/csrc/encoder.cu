@@ -251,15 +251,21 @@ int build_graph(Builder& b) {
     return s.out;
   };
   for (int li = 0; li < 2; ++li) {
-    const float* w1 = &b.enc->bifpn_w[li][0];     // [2][4]
+    // (w1 [2][4], the top-down fusion scalars, is folded into the weights on the host)
     const float* w2 = &b.enc->bifpn_w[li][8];     // [3][4]
     const std::string p = "b" + std::to_string(li) + "_";
     const int p3x = feat[0], p4x = feat[1], p5x = feat[2], p6x = feat[3], p7x = feat[4];
     const int p7td = p7x;
-    const int p6td = b.conv(p + "p6td", fuse(p6x, w1[0], p7td, w1[4 + 0], -1, 0.f), 1, 0, true);
-    const int p5td = b.conv(p + "p5td", fuse(p5x, w1[1], p6td, w1[4 + 1], -1, 0.f), 1, 0, true);
-    const int p4td = b.conv(p + "p4td", fuse(p4x, w1[2], p5td, w1[4 + 2], -1, 0.f), 1, 0, true);
-    const int p3td = b.conv(p + "p3td", fuse(p3x, w1[3], p4td, w1[4 + 3], -1, 0.f), 1, 0, true);
+    // top-down nodes (bifpn.py:111-114): node(w0*a + w1*up(b)) = relu(W0 a + up(W1 b) + shift); the fusion scalars are
+    // folded into the two weight sets on the host, the low-resolution product is added in the epilogue (res_mode 3)
+    auto td_node = [&](const std::string& name, int a, int lower) {
+      const int u = b.conv(name + "_u", lower, 1, 0, false);
+      return b.conv(name, a, 1, 0, true, u, 3);
+    };
+    const int p6td = td_node(p + "p6td", p6x, p7td);
+    const int p5td = td_node(p + "p5td", p5x, p6td);
+    const int p4td = td_node(p + "p4td", p4x, p5td);
+    const int p3td = td_node(p + "p3td", p3x, p4td);
     const int p3out = p3td;
     const int p4out = b.conv(p + "p4out", fuse(p4x, w2[0], p4td, w2[4 + 0], p3out, w2[8 + 0]), 1, 0, true);
     const int p5out = b.conv(p + "p5out", fuse(p5x, w2[1], p5td, w2[4 + 1], p4out, w2[8 + 1]), 1, 0, true);
@@ -445,6 +451,10 @@ int make_plan(dad3d_encoder* enc, int B, void* ws, size_t ws_bytes, bool layout_
     ep.relu = s.relu;
     ep.res_mode = res_in_k ? 0 : s.res_mode;
     ep.res = view(s.res);
+    if (s.res >= 0) {
+      ep.res_h = plan->tensors[s.res].H;
+      ep.res_w = plan->tensors[s.res].W;
+    }
     if (s.res >= 0 && plan->tensors[s.res].C != w->cout_pad) {
       set_error("layer " + w->name + ": residual channel mismatch");
       return DAD3D_ERR_INVALID;
@@ -659,7 +669,8 @@ int dad3d_encoder_create(dad3d_encoder** out, const dad3d_conv_weights* layers, 
         if (ui == 0) need.push_back(p + "id");
       }
     for (int li = 0; li < 2; ++li)
-      for (const char* n : {"p6td", "p5td", "p4td", "p3td", "p4out", "p5out", "p6out", "p7out"})
+      for (const char* n : {"p6td", "p5td", "p4td", "p3td", "p6td_u", "p5td_u", "p4td_u", "p3td_u", "p4out", "p5out",
+                            "p6out", "p7out"})
         need.push_back("b" + std::to_string(li) + "_" + n);
     for (auto& n : need)
       if (!enc->convs.count(n)) { set_error("missing layer weights: " + n); return fail(DAD3D_ERR_INVALID); }

@@ -81,8 +81,10 @@ struct EpiConv {
   struct Params {
     const float* bias;        // [Cout_pad] folded BN shift / conv bias
     int relu;
-    int res_mode;             // 0 none, 1 add before ReLU (ResUnit), 2 multiply after bias (FusionLayer gate)
-    ActView res;              // same pixel indexing as the output
+    int res_mode;             // 0 none, 1 add before ReLU (ResUnit), 2 multiply after bias (FusionLayer gate),
+                              // 3 add a LOWER-RESOLUTION map nearest-up-sampled to the output grid (BiFPN top-down node)
+    ActView res;              // modes 1/2: same pixel indexing as the output; mode 3: [N, res_h, res_w, C]
+    int res_h, res_w;         // mode 3 source extents (src = floor(dst * in / out), F.interpolate nearest)
     uint16_t* out;            // piece planes [planes][pix][ld_out]; may be null when only out_f32 is wanted
     long long out_plane;
     int out_planes;
@@ -138,11 +140,16 @@ struct EpiConv {
     //    a single memory round trip instead of one per plane
     uint4 q[3][4];
     const int planes = ep.res.planes;
+    long long rpix = c.pix;                            // this lane's row in the residual tensor
+    if (ep.res_mode == 3) {
+      const int sh = (c.h * ep.res_h) / c.g->Ho, sw = (c.w * ep.res_w) / c.g->Wo;
+      rpix = (static_cast<long long>(c.n) * ep.res_h + sh) * ep.res_w + sw;
+    }
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
       const int idx = it * 32 + c.lane;
       const int row = idx >> 2, seg = idx & 3;
-      const long long spix = __shfl_sync(0xffffffffu, c.pix, row);
+      const long long spix = __shfl_sync(0xffffffffu, rpix, row);
       const int svalid = __shfl_sync(0xffffffffu, c.valid ? 1 : 0, row);
       const uint16_t* src = ep.res.base + spix * ep.res.C + col + seg * 8;
 #pragma unroll
@@ -200,7 +207,7 @@ struct EpiConv {
       const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col) + j);
       x[4 * j] += b.x; x[4 * j + 1] += b.y; x[4 * j + 2] += b.z; x[4 * j + 3] += b.w;
     }
-    if (ep.res_mode == 1) {
+    if (ep.res_mode == 1 || ep.res_mode == 3) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) x[j] += st.r[H * 32 + j];
     } else if (ep.res_mode == 2) {

@@ -295,25 +295,30 @@ struct EpiLbs {
     const int vb = (c.col0 + colw) / 3;                                          // first vertex of this warp
     const float wl = st.wl;
 
-#pragma unroll 1
+    // ---- the warp's 48 accumulator columns (16 vertices) -> registers in one go, then hand TMEM back immediately
+    float xa[48];
+    {
+      const uint32_t t = c.t_acc + static_cast<uint32_t>(colw);
+      ptx::tmem_ld_32x32b_x32_f(t, xa);
+      ptx::tmem_ld_32x32b_x16_f(t + 32, xa + 32);
+      if (c.g->n_acc == 2) {
+        float b[48];
+        ptx::tmem_ld_32x32b_x32_f(t + c.g->block_n, b);
+        ptx::tmem_ld_32x32b_x16_f(t + c.g->block_n + 32, b + 32);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 48; ++j) xa[j] += b[j];
+      } else {
+        ptx::tmem_ld_wait();
+      }
+    }
+    epi_release_tmem(c);
+
+#pragma unroll
     for (int pass = 0; pass < 2; ++pass) {
       float x[24];                                                               // 8 vertices of this pass
-      {
-        const uint32_t t = c.t_acc + static_cast<uint32_t>(colw + pass * 24);
-        ptx::tmem_ld_32x32b_x16_f(t, x);
-        ptx::tmem_ld_32x32b_x8_f(t + 16, x + 16);
-        if (c.g->n_acc == 2) {                                                   // all four loads in flight, one wait
-          float b[24];
-          ptx::tmem_ld_32x32b_x16_f(t + c.g->block_n, b);
-          ptx::tmem_ld_32x32b_x8_f(t + c.g->block_n + 16, b + 16);
-          ptx::tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 24; ++j) x[j] += b[j];
-        } else {
-          ptx::tmem_ld_wait();
-        }
-      }
-      if (pass == 1) epi_release_tmem(c);
+      for (int j = 0; j < 24; ++j) x[j] = xa[pass * 24 + j];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float px = x[3 * i], py = x[3 * i + 1], pz = x[3 * i + 2];

@@ -68,16 +68,28 @@ def fold_state_dict(sd: Dict[str, Tensor]) -> Tuple[List[Tuple[str, np.ndarray, 
     add("lat7", sd["bifpn.p7.conv.weight"].double() * s[:, None, None, None],
         sd["bifpn.p7.conv.bias"].double() * s + sh)
     fusion_w = np.zeros((2, 20), np.float32)
+    td_col = {"p6_td": 0, "p5_td": 1, "p4_td": 2, "p3_td": 3}                     # column of w1 each top-down node uses
     for li in range(2):
-        for node in ("p6_td", "p5_td", "p4_td", "p3_td", "p4_out", "p5_out", "p6_out", "p7_out"):
-            p = f"bifpn.bifpn.{li}.{node}"
-            s, sh = _bn_scale_shift(sd, p + ".bn", BN_EPS_BIFPN)
-            dw = sd[p + ".depthwise.weight"].double().reshape(1, -1, 1, 1)         # per-input-channel scale
-            add(f"b{li}_{node.replace('_', '')}", sd[p + ".pointwise.weight"].double() * dw * s[:, None, None, None], sh)
+        fw = {}
         for key, off in (("w1", 0), ("w2", 8)):                                    # bifpn.py:105-108, in fp32 like torch
             w = torch.relu(sd[f"bifpn.bifpn.{li}.{key}"].float())
             w = w / torch.sum(w, dim=0) + BIFPN_EPSILON
             fusion_w[li, off:off + w.numel()] = w.reshape(-1).numpy()
+            fw[key] = w.double()
+        for node in ("p6_td", "p5_td", "p4_td", "p3_td", "p4_out", "p5_out", "p6_out", "p7_out"):
+            p = f"bifpn.bifpn.{li}.{node}"
+            s, sh = _bn_scale_shift(sd, p + ".bn", BN_EPS_BIFPN)
+            dw = sd[p + ".depthwise.weight"].double().reshape(1, -1, 1, 1)         # per-input-channel scale
+            wfull = sd[p + ".pointwise.weight"].double() * dw * s[:, None, None, None]
+            name = f"b{li}_{node.replace('_', '')}"
+            if node in td_col:
+                # top-down node: node(w0*a + w1*up(b)) = relu(W(w0 a) + up(W(w1 b)) + shift) because a 1x1 conv commutes with
+                # nearest up-sampling -> two GEMMs (the second at the lower resolution), no separate weighted-sum pass
+                j = td_col[node]
+                add(name, wfull * fw["w1"][0, j], sh)
+                add(name + "_u", wfull * fw["w1"][1, j], torch.zeros_like(sh))
+            else:
+                add(name, wfull, sh)
     add("heat", sd["head.heatmap.weight"].double(), sd["head.heatmap.bias"].double())
     wf = sd["fusion_layer.conv1x1.weight"].double()                                # [1024, 1024+68+256, 1, 1]
     n_heat = sd["head.heatmap.weight"].shape[0]

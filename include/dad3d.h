@@ -102,7 +102,9 @@ DAD3D_API int dad3d_gather_landmarks_bary(const float* src_d, int32_t B, int32_t
  *   "stem" (7x7 3->64)                       encoder.model.init_block.conv
  *   "s{1..4}u{k}c{1,2,3}", "s{i}u1id"        encoder.model.stage{i}.unit{k}.body.conv{1,2,3} / .identity_conv
  *   "lat3".."lat7"                           bifpn.p3 .. bifpn.p7
- *   "b{0,1}_{p6td,p5td,p4td,p3td,p4out,p5out,p6out,p7out}"   bifpn.bifpn.{0,1}.<node> (depthwise scale, pointwise, BN folded)
+ *   "b{0,1}_{p4out,p5out,p6out,p7out}"       bifpn.bifpn.{0,1}.<node> (depthwise scale, pointwise, BN folded)
+ *   "b{0,1}_{p6td,p5td,p4td,p3td}" and "..._u"   top-down nodes split in two: W*(w0 a) at the node's resolution and
+ *                                            W*(w1 b) at the lower one (fusion scalars folded in; the second has no bias)
  *   "heat"                                   head.heatmap (3x3 256->68 + bias)
  *   "fusion"                                 fusion_layer.conv1x1 with K laid out [x 1024 | heat 68 + 60 zero | p5 256]
  *   "mlp1" (2048 -> 3x512)  "mlp2" (block-diagonal 1536 -> 403|10|136)   {shape,pose,landmarks}.logit_image.{0,3}
