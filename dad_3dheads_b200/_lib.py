@@ -55,6 +55,8 @@ SIGNATURES = {
     "dad3d_encoder_set_profile": (C.c_int, [C.c_void_p, C.c_int32]),
     "dad3d_encoder_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong),
                                               C.POINTER(C.c_double)]),
+    "dad3d_encoder_profile_layer": (C.c_int, [C.c_void_p, C.c_int32, C.c_char_p, C.c_int32, C.POINTER(C.c_double),
+                                               C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     "dad3d_encoder_set_debug": (C.c_int, [C.c_void_p, C.c_int32]),
     "dad3d_encoder_read_activation": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t,
                                                  C.POINTER(C.c_int32), C.c_void_p]),

@@ -43,7 +43,8 @@ struct ConvW {
 int pick_block_n(int cout) {
   if (cout % 128 == 0) return 128;
   if (cout % 64 == 0) return 64;
-  return 96;                                  // 68 -> 96, 549 -> 6 x 96
+  if (cout <= 80) return 80;                  // heat-map head: 68 -> one 80-wide tile (UMMA N % 16 == 0)
+  return 96;                                  // 549 -> 6 x 96
 }
 
 inline uint16_t host_bf16(float x) {          // round-to-nearest-even fp32 -> bf16
@@ -81,7 +82,7 @@ struct Step {
   int in = -1, out = -1, res = -1, out_f32 = -1, in2 = -1, in3 = -1;
   // conv
   const ConvW* w = nullptr;
-  int stride = 1, pad = 0, relu = 0, res_mode = 0;
+  int stride = 1, pad = 0, relu = 0, res_mode = 0, res_stride = 1;
   GemmMaps maps;
   GemmGeom geom;
   EpiConv::Params epi;
@@ -121,6 +122,7 @@ struct dad3d_encoder {
   bool profile = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
   size_t prof_used = 0;
+  std::vector<const void*> prof_steps;   // the Step each recorded launch ran (valid while the plan lives)
   double prof_flops = 0.0;         // algorithmic (useful, unpadded, one-product) FLOPs of the recorded launches
   double prof_bytes = 0.0;         // algorithmic HBM bytes of the recorded launches (inputs + weights + outputs once)
 };
@@ -158,8 +160,10 @@ struct Builder {
     return it == enc->convs.end() ? nullptr : &it->second;
   }
   // conv / linear layer; returns the output tensor id (pieces) unless f32_only
+  // res_mode: 0 none, 1 residual add, 2 gate multiply, 3 up-sampled add, 4 second 1x1 source (stride res_stride) whose
+  // weights are K-concatenated behind the layer's own
   int conv(const std::string& name, int in, int stride, int pad, bool relu, int res = -1, int res_mode = 0,
-           bool f32_out = false, bool pieces_out = true, int* f32_id = nullptr) {
+           bool f32_out = false, bool pieces_out = true, int* f32_id = nullptr, int res_stride = 1) {
     const ConvW* w = W(name);
     const TensorInfo ti = plan->tensors[in];
     const int Ho = (ti.H + 2 * pad - w->R) / stride + 1;
@@ -174,6 +178,7 @@ struct Builder {
     s.relu = relu ? 1 : 0;
     s.res = res;
     s.res_mode = res_mode;
+    s.res_stride = res_stride;
     s.out = pieces_out ? tensor(ti.N, Ho, Wo, w->cout_pad) : -1;
     s.out_f32 = f32_out ? tensor(ti.N, Ho, Wo, w->cout_pad, true) : -1;
     if (s.out >= 0) plan->tensors[s.out].name = name;
@@ -217,11 +222,15 @@ int build_graph(Builder& b) {
     for (int ui = 0; ui < kStageUnits[si]; ++ui) {
       const std::string p = "s" + std::to_string(si + 1) + "u" + std::to_string(ui + 1);
       const int stride = (ui == 0 && si != 0) ? 2 : 1;
-      int identity = cur;
-      if (ui == 0) identity = b.conv(p + "id", cur, stride, 0, false);
       int y = b.conv(p + "c1", cur, stride, 0, true);
       y = b.conv(p + "c2", y, 1, 1, true);
-      cur = b.conv(p + "c3", y, 1, 0, true, identity, 1);
+      if (ui == 0) {
+        // first unit of a stage: the projection shortcut (1x1, stride s, BN) is K-concatenated behind the last 1x1 --
+        // out = relu([W3 | Wid] [y ; x_strided] + b3 + bid): one GEMM, the shortcut tensor is never materialised
+        cur = b.conv(p + "c3", y, 1, 0, true, cur, 4, false, true, nullptr, stride);
+      } else {
+        cur = b.conv(p + "c3", y, 1, 0, true, cur, 1);
+      }
     }
     return cur;
   };
@@ -381,9 +390,11 @@ int make_plan(dad3d_encoder* enc, int B, void* ws, size_t ws_bytes, bool layout_
     if (s.kind != kConv) continue;
     const TensorInfo& ti = plan->tensors[s.in];
     const ConvW* w = s.w;
-    if (ti.C != w->cin_pad) {
-      set_error("layer " + w->name + ": input has " + std::to_string(ti.C) + " channels, weights expect " +
-                std::to_string(w->cin_pad));
+    const bool src2 = s.res >= 0 && s.res_mode == 4;
+    const int cin2 = src2 ? plan->tensors[s.res].C : 0;
+    if (ti.C + cin2 != w->cin_pad) {
+      set_error("layer " + w->name + ": input has " + std::to_string(ti.C) + "+" + std::to_string(cin2) +
+                " channels, weights expect " + std::to_string(w->cin_pad));
       return DAD3D_ERR_INVALID;
     }
     const int Ho = (ti.H + 2 * s.pad - w->R) / s.stride + 1;
@@ -397,7 +408,7 @@ int make_plan(dad3d_encoder* enc, int B, void* ws, size_t ws_bytes, bool layout_
     g.Wo = Wo; g.Ho = Ho; g.Nimg = ti.N;
     g.stride = s.stride;
     g.R = w->R; g.S = w->S; g.pad_h = s.pad; g.pad_w = s.pad;
-    g.cin_blocks = w->cin_pad / kBlockK;
+    g.cin_blocks = ti.C / kBlockK;                    // main source; a second source adds res_kb blocks below
     g.cl_m = 1; g.cl_n = 1;
     const bool res_in_k = s.res >= 0 && s.res_mode == 1 && w->has_identity;
     // few row tiles (small maps / small batch): halve the tile width so that twice as many CTAs share the work
@@ -419,6 +430,11 @@ int make_plan(dad3d_encoder* enc, int B, void* ws, size_t ws_bytes, bool layout_
         g.mma_res_acc[i] = (enc->n_acc == 2 && g.mma_res_a[i] != 0) ? 1 : 0;
       }
     }
+    if (src2) {                                       // projection shortcut as a second K segment
+      g.res_kb = cin2 / kBlockK;
+      g.res_kind = 1;
+      g.res_stride = s.res_stride;
+    }
     g.stages = gemm_max_stages(g);
     if (g.stages < 2) { set_error("layer " + w->name + ": pipeline does not fit shared memory"); return DAD3D_ERR_INVALID; }
     for (int p = 0; p < enc->P; ++p) {
@@ -433,29 +449,32 @@ int make_plan(dad3d_encoder* enc, int B, void* ws, size_t ws_bytes, bool layout_
       if (!make_tmap_16bit(&s.maps.a[p], basep, 4, dims, strides, box, es)) return DAD3D_ERR_CUDA;
       s.maps.b[p] = narrow ? w->map_b64[p] : w->map_b[p];
     }
-    if (res_in_k) {
+    if (res_in_k || src2) {
       const TensorInfo& tr = plan->tensors[s.res];
+      const int rs = src2 ? s.res_stride : 1;
       for (int p = 0; p < enc->P; ++p) {
         const uint64_t dims[4] = {static_cast<uint64_t>(tr.C), static_cast<uint64_t>(tr.W), static_cast<uint64_t>(tr.H),
                                   static_cast<uint64_t>(tr.N)};
         const uint64_t strides[3] = {static_cast<uint64_t>(tr.C) * 2, static_cast<uint64_t>(tr.W) * tr.C * 2,
                                      static_cast<uint64_t>(tr.H) * tr.W * tr.C * 2};
-        const uint32_t box[4] = {kBlockK, static_cast<uint32_t>(g.tw), static_cast<uint32_t>(g.th), static_cast<uint32_t>(g.tn)};
+        const uint32_t box[4] = {kBlockK, static_cast<uint32_t>(g.tw * rs), static_cast<uint32_t>(g.th * rs),
+                                 static_cast<uint32_t>(g.tn)};
+        const uint32_t es[4] = {1, static_cast<uint32_t>(rs), static_cast<uint32_t>(rs), 1};
         const uint16_t* basep = reinterpret_cast<const uint16_t*>(tr.ptr) + static_cast<size_t>(p) * tr.plane_elems();
-        if (!make_tmap_16bit(&s.maps.r[p], basep, 4, dims, strides, box, nullptr)) return DAD3D_ERR_CUDA;
+        if (!make_tmap_16bit(&s.maps.r[p], basep, 4, dims, strides, box, es)) return DAD3D_ERR_CUDA;
       }
     }
     EpiConv::Params& ep = s.epi;
     std::memset(&ep, 0, sizeof(ep));
     ep.bias = w->d_bias;
     ep.relu = s.relu;
-    ep.res_mode = res_in_k ? 0 : s.res_mode;
+    ep.res_mode = (res_in_k || src2) ? 0 : s.res_mode;
     ep.res = view(s.res);
     if (s.res >= 0) {
       ep.res_h = plan->tensors[s.res].H;
       ep.res_w = plan->tensors[s.res].W;
     }
-    if (s.res >= 0 && plan->tensors[s.res].C != w->cout_pad) {
+    if (s.res >= 0 && !src2 && plan->tensors[s.res].C != w->cout_pad) {
       set_error("layer " + w->name + ": residual channel mismatch");
       return DAD3D_ERR_INVALID;
     }
@@ -521,6 +540,8 @@ int launch_conv(dad3d_encoder* enc, const Step& s, cudaStream_t stream) {
       DAD3D_CUDA_OK(cudaEventCreate(&b));
       enc->prof_events.emplace_back(a, b);
     }
+    if (enc->prof_steps.size() <= enc->prof_used) enc->prof_steps.resize(enc->prof_used + 1);
+    enc->prof_steps[enc->prof_used] = &s;
     ev = &enc->prof_events[enc->prof_used++];
     enc->prof_flops += conv_useful_flops(s);
     DAD3D_CUDA_OK(cudaEventRecord(ev->first, stream));
@@ -613,7 +634,9 @@ int dad3d_encoder_create(dad3d_encoder** out, const dad3d_conv_weights* layers, 
     cw.cout_pad = ceil_div(L.cout, cw.block_n) * cw.block_n;
     cw.cin_pad = ceil_div(L.cin, kBlockK) * kBlockK;
     // the last 1x1 of a ResUnit ("...c3") gets identity columns appended to its K axis: [W | I] * [a ; residual]
-    cw.has_identity = name.size() > 2 && name.compare(name.size() - 2, 2, "c3") == 0 && L.R == 1 && L.S == 1;
+    // (the first unit's c3 carries the projection-shortcut weights in its K axis instead and needs no identity)
+    cw.has_identity = name.size() > 4 && name.compare(name.size() - 2, 2, "c3") == 0 && L.R == 1 && L.S == 1 &&
+                      name.compare(name.size() - 4, 4, "u1c3") != 0;
     const size_t ktot_main = static_cast<size_t>(L.R) * L.S * cw.cin_pad;
     const size_t ktot = ktot_main + (cw.has_identity ? cw.cout_pad : 0);
     const size_t plane = static_cast<size_t>(cw.cout_pad) * ktot;
@@ -666,7 +689,6 @@ int dad3d_encoder_create(dad3d_encoder** out, const dad3d_conv_weights* layers, 
       for (int ui = 0; ui < kStageUnits[si]; ++ui) {
         const std::string p = "s" + std::to_string(si + 1) + "u" + std::to_string(ui + 1);
         need.push_back(p + "c1"); need.push_back(p + "c2"); need.push_back(p + "c3");
-        if (ui == 0) need.push_back(p + "id");
       }
     for (int li = 0; li < 2; ++li)
       for (const char* n : {"p6td", "p5td", "p4td", "p3td", "p6td_u", "p5td_u", "p4td_u", "p3td_u", "p4out", "p5out",
@@ -827,6 +849,45 @@ int dad3d_encoder_profile_read(dad3d_encoder* enc, double* gemm_ms, long long* g
   *useful_flops = enc->prof_flops;
   enc->prof_used = 0;
   enc->prof_flops = 0.0;
+  return DAD3D_OK;
+}
+
+int dad3d_encoder_profile_layer(dad3d_encoder* enc, int32_t index, char* name, int32_t name_cap, double* ms,
+                                double* useful_flops, double* algo_bytes, int32_t* info8) {
+  DAD3D_REQUIRE(enc && name && name_cap > 0 && ms && useful_flops && algo_bytes && info8, "null pointer");
+  DAD3D_REQUIRE(enc->plan, "no forward has run yet");
+  if (index < 0 || static_cast<size_t>(index) >= enc->prof_used) return DAD3D_ERR_INVALID;   // end of list (no message)
+  const Step& s = *static_cast<const Step*>(enc->prof_steps[index]);
+  const GemmGeom& g = s.geom;
+  DAD3D_CUDA_OK(cudaEventSynchronize(enc->prof_events[index].second));
+  float t = 0.f;
+  DAD3D_CUDA_OK(cudaEventElapsedTime(&t, enc->prof_events[index].first, enc->prof_events[index].second));
+  *ms = t;
+  *useful_flops = conv_useful_flops(s);
+  std::snprintf(name, static_cast<size_t>(name_cap), "%s", s.w->name.c_str());
+  const Plan& plan = *enc->plan;
+  auto bytes_of = [&](int id) -> double {
+    if (id < 0) return 0.0;
+    const TensorInfo& t = plan.tensors[id];
+    const double elems = static_cast<double>(t.N) * t.H * t.W * t.C;
+    return t.f32 ? elems * 4.0 : elems * 2.0 * t.planes;
+  };
+  // every operand once: input map (strided convs read 1/stride^2 of it only for 1x1), residual / second source, weight
+  // pieces, outputs
+  double in_b = bytes_of(s.in);
+  if (s.w->R == 1 && g.stride > 1) in_b /= static_cast<double>(g.stride) * g.stride;
+  double res_b = bytes_of(s.res);
+  if (g.res_kind == 1 && g.res_stride > 1) res_b /= static_cast<double>(g.res_stride) * g.res_stride;
+  const double w_b = static_cast<double>(s.w->cout_pad) * s.w->R * s.w->S * s.w->cin_pad * 2.0 * enc->P;
+  *algo_bytes = in_b + res_b + w_b + bytes_of(s.out) + bytes_of(s.out_f32);
+  info8[0] = g.Nimg * g.Ho * g.Wo;                       // M: output pixels
+  info8[1] = s.w->cin * s.w->R * s.w->S;                 // K (as given, before padding)
+  info8[2] = s.w->cout;                                  // N
+  info8[3] = g.n_mma;                                    // tensor-core products per MAC
+  info8[4] = g.tiles_w * g.tiles_h * g.tiles_n * g.n_tiles;
+  info8[5] = g.block_n;
+  info8[6] = g.stages;
+  info8[7] = g.cin_blocks * g.R * g.S + g.res_kb;        // k-blocks per tile
   return DAD3D_OK;
 }
 

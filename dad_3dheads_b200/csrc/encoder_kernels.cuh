@@ -99,13 +99,16 @@ struct EpiConv {
     if (cb >= ce) epi_release_tmem(c);
     for (int ch = cb; ch < ce; ++ch) {
       float x[32];
-      epi_load32<0>(c, ch * 32, x);
+      const bool tail16 = ch * 32 + 32 > c.g->block_n;            // 16-column last chunk (block_n = 80)
+      if (tail16) epi_load16<0>(c, ch * 32, x);
+      else epi_load32<0>(c, ch * 32, x);
       if (ch == ce - 1) epi_release_tmem(c);
       if (!c.valid) continue;
       const int col = c.col0 + ch * 32;
       float4* d = reinterpret_cast<float4*>(ep.out_f32 + c.pix * ep.ld_f32 + col);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
+        if (tail16 && j >= 4) break;
         const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col) + j);
         float4 o = make_float4(x[4 * j] + b.x, x[4 * j + 1] + b.y, x[4 * j + 2] + b.z, x[4 * j + 3] + b.w);
         if (ep.relu) {
@@ -116,9 +119,6 @@ struct EpiConv {
     }
   }
 
-  // piece outputs: NC = block_n / 2 columns per warp (32 or 64).  The warp's 32 rows x NC channels are staged in its
-  // private shared-memory tile in the TMA swizzle pattern and written with ONE bulk tensor store per piece plane
-  // (out-of-range rows of partial tiles are clipped by the tensor map).
   // The warp's columns are handled in halves of 32 channels (block_n 128 -> two halves per warp, block_n 64 -> one), which
   // keeps the per-thread working set at 32 accumulator values (+ the prefetched residual).  Staging rows are 64 bytes
   // (TMA SWIZZLE_64B pattern: 16-byte chunk index XOR ((row >> 1) & 3)).
@@ -467,7 +467,8 @@ __global__ void gap_kernel(ActView x, int B, int HW, int C, uint16_t* __restrict
   float acc[8], t[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-  for (int p = 0; p < HW; ++p) {
+#pragma unroll 4
+  for (int p = 0; p < HW; ++p) {                    // (unrolled: several pixels' loads in flight per thread)
     act_load8(x, (static_cast<long long>(b) * HW + p) * C + cg * 8, t);
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] += t[j];

@@ -60,6 +60,11 @@ struct GemmGeom {
                                    // tile's own channel range) and whose B tiles are the identity columns appended to the
                                    // packed weights -- the tensor core performs "+ identity(x)" and the residual rides the
                                    // TMA pipeline (deep prefetch, no epilogue loads).  0 = off.
+  int res_kind;                    // 0: identity residual as described; 1: SECOND CONV SOURCE -- res_kb k-blocks of a 1x1
+                                   // convolution over another tensor (maps.r, element stride res_stride) whose weights
+                                   // are K-concatenated behind the main ones: D = [W | W2] [a ; a2] (projection shortcut
+                                   // fused into the last conv of a ResUnit).  All B pieces, the full product list.
+  int res_stride;
   int n_mma_res;                   // products issued for a residual k-block: (mma_res_a[i], B piece 0) -> mma_res_acc[i]
   int mma_res_a[kMaxPieces], mma_res_acc[kMaxPieces];
   int stages;                      // smem ring depth
@@ -207,7 +212,7 @@ __device__ __forceinline__ void epi_release_tmem(const EpiCtx& c) {
 }
 // 32-column chunks [cb, ce) of the tile that column group grp handles
 __device__ __forceinline__ void epi_chunk_range(const GemmGeom& g, int grp, int* cb, int* ce) {
-  const int nch = g.block_n / 32;
+  const int nch = (g.block_n + 31) / 32;          // the last chunk may be 16 columns wide (block_n = 80)
   const int per = (nch + 1) / 2;
   *cb = grp * per;
   *ce = min(nch, *cb + per);
@@ -283,16 +288,30 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
       TileCoord tc;
       for (int ti = 0; tile_at(g, ti, &tc); ++ti) {
         for (int kb = 0; kb < num_kb + g.res_kb; ++kb) {
-          if (kb >= num_kb) {                      // residual k-block: A = residual tile, B = identity columns
+          if (kb >= num_kb) {                      // extra k-blocks fed from the second tensor (maps.r)
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
-            // only B piece 0 carries the identity (the other planes are zero there and are never multiplied)
-            ptx::mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(g.nA * kTileABytes + g.block_n * kBlockK * 2));
             uint8_t* st = smem + stage * stage_bytes;
-            const int rc = tc.n_tile * g.block_n + (kb - num_kb) * kBlockK;
-            for (int i = 0; i < g.nA; ++i)
-              ptx::tma_load_4d(st + i * kTileABytes, &maps.r[i], &full_bar[stage], rc, tc.w0, tc.h0, tc.n0);
-            ptx::tma_load_2d(st + g.nA * kTileABytes, &maps.b[0], &full_bar[stage], num_kb * kBlockK + rc,
-                             tc.n_tile * g.block_n);
+            const int r = kb - num_kb;
+            if (g.res_kind == 0) {
+              // identity residual: A = residual tile (the tile's own channels), B = identity columns (piece 0 only: the
+              // other planes are zero there and are never multiplied)
+              ptx::mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(g.nA * kTileABytes + g.block_n * kBlockK * 2));
+              const int rc = tc.n_tile * g.block_n + r * kBlockK;
+              for (int i = 0; i < g.nA; ++i)
+                ptx::tma_load_4d(st + i * kTileABytes, &maps.r[i], &full_bar[stage], rc, tc.w0, tc.h0, tc.n0);
+              ptx::tma_load_2d(st + g.nA * kTileABytes, &maps.b[0], &full_bar[stage], num_kb * kBlockK + rc,
+                               tc.n_tile * g.block_n);
+            } else {
+              // second 1x1 source: A = 64 channels of the other tensor at (strided) pixel coordinates, B = its weights
+              ptx::mbar_expect_tx(&full_bar[stage], tx_bytes);
+              for (int i = 0; i < g.nA; ++i)
+                ptx::tma_load_4d(st + i * kTileABytes, &maps.r[i], &full_bar[stage], r * kBlockK, tc.w0 * g.res_stride,
+                                 tc.h0 * g.res_stride, tc.n0);
+              uint8_t* sb2 = st + g.nA * kTileABytes;
+              for (int i = 0; i < g.nB; ++i)
+                ptx::tma_load_2d(sb2 + i * g.block_n * kBlockK * 2, &maps.b[i], &full_bar[stage], (num_kb + r) * kBlockK,
+                                 tc.n_tile * g.block_n);
+            }
             if (++stage == g.stages) { stage = 0; phase ^= 1u; }
             continue;
           }
@@ -346,7 +365,7 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
           ptx::tc_fence_after();
           const uint32_t sa = ptx::smem_u32(smem + stage * stage_bytes);
           const uint32_t sb = sa + g.nA * kTileABytes;
-          const bool res_block = kb >= num_kb;
+          const bool res_block = kb >= num_kb && g.res_kind == 0;    // a second conv source uses the normal product list
           const int n_prod = res_block ? g.n_mma_res : g.n_mma;
           for (int i = 0; i < n_prod; ++i) {
             const int pa = res_block ? g.mma_res_a[i] : g.mma_a[i];

@@ -59,9 +59,15 @@ def fold_state_dict(sd: Dict[str, Tensor]) -> Tuple[List[Tuple[str, np.ndarray, 
             n = f"s{si + 1}u{ui + 1}"
             conv_bn(n + "c1", p + ".body.conv1")
             conv_bn(n + "c2", p + ".body.conv2")
-            conv_bn(n + "c3", p + ".body.conv3")
             if ui == 0:
-                conv_bn(n + "id", p + ".identity_conv")
+                # projection shortcut fused into the last 1x1: out = relu([W3 | Wid] [y ; x] + b3 + bid)
+                s3, sh3 = _bn_scale_shift(sd, p + ".body.conv3.bn", BN_EPS_RESNET)
+                si_, shi = _bn_scale_shift(sd, p + ".identity_conv.bn", BN_EPS_RESNET)
+                w3 = sd[p + ".body.conv3.conv.weight"].double() * s3[:, None, None, None]
+                wi = sd[p + ".identity_conv.conv.weight"].double() * si_[:, None, None, None]
+                add(n + "c3", torch.cat([w3, wi], dim=1), sh3 + shi)
+            else:
+                conv_bn(n + "c3", p + ".body.conv3")
     for lvl in (3, 4, 5, 6):
         add(f"lat{lvl}", sd[f"bifpn.p{lvl}.weight"].double(), sd[f"bifpn.p{lvl}.bias"].double())
     s, sh = _bn_scale_shift(sd, "bifpn.p7.bn", BN_EPS_BIFPN)       # BiFPNConvBlock: conv(bias) -> BN -> ReLU
@@ -177,6 +183,20 @@ class Dad3dEncoder:
         _lib.check(self.lib.dad3d_encoder_profile_read(self._h, C.byref(ms), C.byref(n), C.byref(fl)),
                    "dad3d_encoder_profile_read")
         return ms.value, n.value, fl.value
+
+    def profile_layers(self):
+        """Per-launch records of the current profiling window (call before :meth:`profile_read`): list of dicts with
+        name, ms, flops (useful), bytes (algorithmic HBM), M, K, N, products, tiles, block_n, stages, k_blocks."""
+        out = []
+        name = C.create_string_buffer(64)
+        ms, fl, by = C.c_double(), C.c_double(), C.c_double()
+        info = (C.c_int32 * 8)()
+        i = 0
+        while self.lib.dad3d_encoder_profile_layer(self._h, i, name, 64, C.byref(ms), C.byref(fl), C.byref(by), info) == 0:
+            out.append(dict(name=name.value.decode(), ms=ms.value, flops=fl.value, bytes=by.value, M=info[0], K=info[1],
+                            N=info[2], products=info[3], tiles=info[4], block_n=info[5], stages=info[6], k_blocks=info[7]))
+            i += 1
+        return out
 
     # ---- test hooks (include/dad3d.h "test hooks")
     def set_debug(self, keep_all: bool = True) -> None:

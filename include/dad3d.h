@@ -149,6 +149,13 @@ DAD3D_API int dad3d_encoder_set_profile(dad3d_encoder* enc, int32_t on);
 DAD3D_API int dad3d_encoder_profile_read(dad3d_encoder* enc, double* gemm_ms, long long* gemm_launches,
                                          double* useful_flops);
 
+/* One recorded launch of the current profiling window (call BEFORE dad3d_encoder_profile_read, which clears the window):
+ * layer name, device time, useful FLOPs, algorithmic HBM bytes (every operand once), and info8 = {M output pixels, K, N,
+ * tensor-core products per MAC, tiles, tile N, pipeline stages, k-blocks per tile}.  Returns DAD3D_ERR_INVALID past the
+ * last recorded launch. */
+DAD3D_API int dad3d_encoder_profile_layer(dad3d_encoder* enc, int32_t index, char* name, int32_t name_cap, double* ms,
+                                          double* useful_flops, double* algo_bytes, int32_t* info8);
+
 /* test hooks: keep_all != 0 disables workspace reuse so that, after a forward, any activation can be read back by the
  * name of the layer that produced it ("stem", "s2u1c3", "b1_p4out", "cat", "fusion", "gap", "heat", "mlp2" ...) as fp32
  * NHWC with channels padded as stored; dims4 receives [N,H,W,C] (pass out_d = NULL to query the shape only). */

@@ -39,10 +39,12 @@ def run_folded(x: torch.Tensor, layers, fusion_w: np.ndarray, dtype=torch.float6
         for ui in range(STAGE_UNITS[si]):
             p = f"s{si + 1}u{ui + 1}"
             stride = 2 if (ui == 0 and si != 0) else 1
-            ident = conv(p + "id", t, stride) if ui == 0 else t
             u = conv(p + "c1", t, stride, 0, True)
             u = conv(p + "c2", u, 1, 1, True)
-            t = conv(p + "c3", u, 1, 0, True, res=ident)
+            if ui == 0:          # projection shortcut K-concatenated: [W3 | Wid] [u ; t_strided]
+                t = conv(p + "c3", torch.cat([u, t[:, :, ::stride, ::stride]], 1), 1, 0, True)
+            else:
+                t = conv(p + "c3", u, 1, 0, True, res=t)
         return t
 
     c2 = stage(0, y)
