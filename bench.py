@@ -242,7 +242,7 @@ def run_ours(args):
         value = heads / (ms_total * 1e-3)
         e2e_value = heads / (ms_e2e * 1e-3)
         gemm_ms, gemm_launches, useful_flops = prof
-        products = {"fp32": 6, "bf16x3": 6, "bf16x2": 3, "bf16": 1}[args.precision]
+        products = {"fp32": 6, "bf16x3": 6, "bf16x2": 3, "bf16": 1, "fp16x2": 3, "fp16": 1}[args.precision]
         achieved = useful_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
         peak = peaks["bf16_tflops_sustained"]
         traffic, traffic_src = _traffic_from_profile()
@@ -391,7 +391,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="images per GPU per step")
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16x2", "bf16"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16x3", "fp16x2", "bf16x2", "fp16", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="pipeline", choices=["pipeline", "decode"],
                     help="pipeline = configs[1] (headline); decode = configs[4] decode-only microbench")

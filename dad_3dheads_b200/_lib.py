@@ -44,7 +44,8 @@ SIGNATURES = {
                                           C.c_void_p, C.c_void_p]),
     "dad3d_gather_landmarks_bary": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                                C.c_int32, C.c_void_p, C.c_void_p]),
-    "dad3d_encoder_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32]),
+    "dad3d_encoder_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
+                                       C.c_int32]),
     "dad3d_encoder_destroy": (None, [C.c_void_p]),
     "dad3d_encoder_num_layers": (C.c_int, [C.c_void_p]),
     "dad3d_encoder_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int32]),

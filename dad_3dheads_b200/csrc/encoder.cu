@@ -34,6 +34,7 @@ struct ConvW {
   int cout_pad = 0, cin_pad = 0, block_n = 0;
   uint16_t* d_w = nullptr;      // [P][cout_pad][R*S*cin_pad] bf16 pieces
   float* d_bias = nullptr;      // [cout_pad]
+  float* d_scale = nullptr;     // [cout_pad] 2^-s per output channel (fp16 pieces: weights are stored as w * 2^s)
   CUtensorMap map_b[kMaxPieces];      // box 64 x block_n
   CUtensorMap map_b64[kMaxPieces];    // box 64 x 64 (small problems: more, narrower tiles to fill the SMs)
   bool has_b64 = false;
@@ -54,6 +55,8 @@ inline uint16_t host_bf16(float x) {          // round-to-nearest-even fp32 -> b
   u += 0x7fffu + ((u >> 16) & 1u);
   return static_cast<uint16_t>(u >> 16);
 }
+inline uint16_t host_f16(float x) { return __half_as_ushort(__float2half_rn(x)); }   // RN, subnormals kept
+inline float host_f16_to_f32(uint16_t b) { return __half2float(__ushort_as_half(b)); }
 inline float host_bf16_to_f32(uint16_t b) {
   uint32_t u = static_cast<uint32_t>(b) << 16;
   float f;
@@ -106,6 +109,7 @@ struct dad3d_encoder {
   int device = 0;
   int num_sms = 0;
   int P = 3;                       // pieces per operand
+  int fp16 = 0;                    // piece format: 0 = bf16 (1-3 pieces), 1 = fp16 hi/lo (per-channel scaled weights)
   int n_mma = 6;
   int n_acc = 2;
   int mma_a[kMaxMma], mma_b[kMaxMma], mma_acc[kMaxMma];
@@ -377,7 +381,7 @@ int make_plan(dad3d_encoder* enc, int B, void* ws, size_t ws_bytes, bool layout_
   plan->ws_bytes = ws_bytes;
 
   auto view = [&](int id) {
-    ActView v{nullptr, 0, 0, 0};
+    ActView v{nullptr, 0, 0, 0, enc->fp16};
     if (id < 0) return v;
     const TensorInfo& t = plan->tensors[id];
     v.base = reinterpret_cast<const uint16_t*>(t.ptr);
@@ -421,7 +425,7 @@ int make_plan(dad3d_encoder* enc, int B, void* ws, size_t ws_bytes, bool layout_
     g.n_mma = enc->n_mma;
     g.n_acc = enc->n_acc;
     for (int i = 0; i < enc->n_mma; ++i) { g.mma_a[i] = enc->mma_a[i]; g.mma_b[i] = enc->mma_b[i]; g.mma_acc[i] = enc->mma_acc[i]; }
-    g.fmt16 = 1;
+    g.fmt16 = enc->fp16 ? 0u : 1u;
     if (res_in_k) {                                   // "+ identity(x)" performed by the tensor core
       g.res_kb = block_n / kBlockK;
       g.n_mma_res = enc->P;
@@ -467,6 +471,7 @@ int make_plan(dad3d_encoder* enc, int B, void* ws, size_t ws_bytes, bool layout_
     EpiConv::Params& ep = s.epi;
     std::memset(&ep, 0, sizeof(ep));
     ep.bias = w->d_bias;
+    ep.scale = w->d_scale;
     ep.relu = s.relu;
     ep.res_mode = (res_in_k || src2) ? 0 : s.res_mode;
     ep.res = view(s.res);
@@ -527,6 +532,7 @@ int launch_conv(dad3d_encoder* enc, const Step& s, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
     DAD3D_CUDA_OK(cudaFuncSetAttribute(tile_gemm_kernel<EpiConv>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemLimit));
+    DAD3D_CUDA_OK(cudaFuncSetAttribute(tile_gemm_kernel<EpiConvH>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemLimit));
     configured = true;
   }
   const GemmGeom& g = s.geom;
@@ -557,7 +563,8 @@ int launch_conv(dad3d_encoder* enc, const Step& s, cudaStream_t stream) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = enc->use_pdl ? 1 : 0;
-    DAD3D_CUDA_OK(cudaLaunchKernelEx(&cfg, tile_gemm_kernel<EpiConv>, s.maps, g, s.epi));
+    if (enc->fp16) DAD3D_CUDA_OK(cudaLaunchKernelEx(&cfg, tile_gemm_kernel<EpiConvH>, s.maps, g, s.epi));
+    else DAD3D_CUDA_OK(cudaLaunchKernelEx(&cfg, tile_gemm_kernel<EpiConv>, s.maps, g, s.epi));
   }
   count_launch();
   if (ev) DAD3D_CUDA_OK(cudaEventRecord(ev->second, stream));
@@ -571,9 +578,11 @@ int launch_conv(dad3d_encoder* enc, const Step& s, cudaStream_t stream) {
 extern "C" {
 
 int dad3d_encoder_create(dad3d_encoder** out, const dad3d_conv_weights* layers, int32_t n_layers,
-                         const float* bifpn_fusion_w_h, int32_t pieces, int32_t device) {
+                         const float* bifpn_fusion_w_h, int32_t pieces, int32_t operand_format, int32_t device) {
   DAD3D_REQUIRE(out && layers && bifpn_fusion_w_h, "null pointer");
-  DAD3D_REQUIRE(pieces >= 1 && pieces <= 3, "pieces must be 1 (bf16), 2 (bf16x2, 3 products) or 3 (bf16x3, 6 products)");
+  DAD3D_REQUIRE(pieces >= 1 && pieces <= 3, "pieces must be 1 (one product), 2 (hi/lo, 3 products) or 3 (bf16x3, 6 products)");
+  DAD3D_REQUIRE(operand_format == DAD3D_OPERAND_BF16 || (operand_format == DAD3D_OPERAND_FP16 && pieces <= 2),
+                "operand_format must be DAD3D_OPERAND_BF16, or DAD3D_OPERAND_FP16 with 1 or 2 pieces");
   DAD3D_CUDA_OK(cudaSetDevice(device));
   cudaDeviceProp prop;
   DAD3D_CUDA_OK(cudaGetDeviceProperties(&prop, device));
@@ -585,6 +594,7 @@ int dad3d_encoder_create(dad3d_encoder** out, const dad3d_conv_weights* layers, 
   enc->device = device;
   enc->num_sms = prop.multiProcessorCount;
   enc->P = pieces;
+  enc->fp16 = operand_format == DAD3D_OPERAND_FP16 ? 1 : 0;
   // product list, smallest terms first so they are not swamped in the fp32 accumulator
   if (pieces == 1) {
     enc->n_mma = 1; enc->n_acc = 1; enc->mma_a[0] = 0; enc->mma_b[0] = 0; enc->mma_acc[0] = 0;
@@ -641,26 +651,46 @@ int dad3d_encoder_create(dad3d_encoder** out, const dad3d_conv_weights* layers, 
     const size_t ktot = ktot_main + (cw.has_identity ? cw.cout_pad : 0);
     const size_t plane = static_cast<size_t>(cw.cout_pad) * ktot;
     std::vector<uint16_t> packed(plane * pieces, 0);
+    // fp16 pieces: row o is stored as w * 2^s_o with max |w * 2^s_o| <= 2^15 (s_o <= 15 so that the identity entry 2^s_o
+    // stays representable); the epilogue multiplies the accumulator by 2^-s_o (exact).  bf16 pieces: s_o = 0.
+    std::vector<float> scale(cw.cout_pad, 1.f), up(cw.cout_pad, 1.f);
+    if (enc->fp16)
+      for (int o = 0; o < L.cout; ++o) {
+        float amax = 0.f;
+        const float* row = L.weight_h + static_cast<size_t>(o) * L.R * L.S * L.cin;
+        for (size_t i = 0; i < static_cast<size_t>(L.R) * L.S * L.cin; ++i) amax = std::max(amax, std::fabs(row[i]));
+        int e = 0;
+        if (amax > 0.f && std::isfinite(amax)) {
+          std::frexp(amax, &e);                       // amax = m * 2^e, m in [0.5, 1)  ->  amax * 2^(15 - e) in [2^14, 2^15)
+          e = std::min(15, 15 - e);
+          e = std::max(e, -100);
+        }
+        up[o] = std::ldexp(1.f, e);
+        scale[o] = std::ldexp(1.f, -e);
+      }
     if (cw.has_identity)
-      for (int o = 0; o < cw.cout_pad; ++o) packed[static_cast<size_t>(o) * ktot + ktot_main + o] = 0x3F80;   // bf16 1.0, piece 0
+      for (int o = 0; o < cw.cout_pad; ++o)
+        packed[static_cast<size_t>(o) * ktot + ktot_main + o] = enc->fp16 ? host_f16(up[o]) : static_cast<uint16_t>(0x3F80);   // piece 0
     for (int o = 0; o < L.cout; ++o)
       for (int t = 0; t < L.R * L.S; ++t)
         for (int c = 0; c < L.cin; ++c) {
-          float r = L.weight_h[(static_cast<size_t>(o) * L.R * L.S + t) * L.cin + c];
+          float r = L.weight_h[(static_cast<size_t>(o) * L.R * L.S + t) * L.cin + c] * up[o];
           const size_t idx = static_cast<size_t>(o) * ktot + static_cast<size_t>(t) * cw.cin_pad + c;
           for (int p = 0; p < pieces; ++p) {
-            const uint16_t h = host_bf16(r);
+            const uint16_t h = enc->fp16 ? host_f16(r) : host_bf16(r);
             packed[p * plane + idx] = h;
-            r -= host_bf16_to_f32(h);
+            r -= enc->fp16 ? host_f16_to_f32(h) : host_bf16_to_f32(h);
           }
         }
     std::vector<float> bias(cw.cout_pad, 0.f);
     for (int o = 0; o < L.cout; ++o) bias[o] = L.bias_h[o];
     if (cudaMalloc(&cw.d_w, packed.size() * 2) != cudaSuccess || cudaMalloc(&cw.d_bias, bias.size() * 4) != cudaSuccess ||
+        cudaMalloc(&cw.d_scale, scale.size() * 4) != cudaSuccess ||
+        cudaMemcpy(cw.d_scale, scale.data(), scale.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(cw.d_w, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(cw.d_bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
       set_error("weight upload failed for " + name);
-      cudaFree(cw.d_w); cudaFree(cw.d_bias);
+      cudaFree(cw.d_w); cudaFree(cw.d_bias); cudaFree(cw.d_scale);
       return fail(DAD3D_ERR_CUDA);
     }
     for (int p = 0; p < pieces; ++p) {
@@ -668,13 +698,13 @@ int dad3d_encoder_create(dad3d_encoder** out, const dad3d_conv_weights* layers, 
       const uint64_t strides[1] = {static_cast<uint64_t>(ktot) * 2};
       const uint32_t box[2] = {kBlockK, static_cast<uint32_t>(cw.block_n)};
       if (!make_tmap_16bit(&cw.map_b[p], cw.d_w + p * plane, 2, dims, strides, box, nullptr)) {
-        cudaFree(cw.d_w); cudaFree(cw.d_bias);
+        cudaFree(cw.d_w); cudaFree(cw.d_bias); cudaFree(cw.d_scale);
         return fail(DAD3D_ERR_CUDA);
       }
       if (cw.block_n == 128) {
         const uint32_t box64[2] = {kBlockK, 64};
         if (!make_tmap_16bit(&cw.map_b64[p], cw.d_w + p * plane, 2, dims, strides, box64, nullptr)) {
-          cudaFree(cw.d_w); cudaFree(cw.d_bias);
+          cudaFree(cw.d_w); cudaFree(cw.d_bias); cudaFree(cw.d_scale);
           return fail(DAD3D_ERR_CUDA);
         }
         cw.has_b64 = true;
@@ -707,6 +737,7 @@ void dad3d_encoder_destroy(dad3d_encoder* enc) {
   for (auto& kv : enc->convs) {
     cudaFree(kv.second.d_w);
     cudaFree(kv.second.d_bias);
+    cudaFree(kv.second.d_scale);
   }
   cudaFree(enc->d_stem_w);
   cudaFree(enc->d_stem_b);
@@ -741,7 +772,7 @@ int dad3d_encoder_forward(dad3d_encoder* enc, const float* images_d, int32_t B, 
   auto T = [&](int id) -> const TensorInfo& { return plan.tensors[id]; };
   auto view = [&](int id) {
     const TensorInfo& t = T(id);
-    return ActView{reinterpret_cast<const uint16_t*>(t.ptr), t.plane_elems(), t.planes, t.C};
+    return ActView{reinterpret_cast<const uint16_t*>(t.ptr), t.plane_elems(), t.planes, t.C, enc->fp16};
   };
   for (const Step& s : plan.steps) {
     switch (s.kind) {
@@ -764,7 +795,7 @@ int dad3d_encoder_forward(dad3d_encoder* enc, const float* images_d, int32_t B, 
         const long long total = static_cast<long long>(B) * to.H * to.W * 8;
         stem_pool_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
             reinterpret_cast<const float*>(ti.ptr), B, ti.H, ti.W, reinterpret_cast<uint16_t*>(to.ptr), to.plane_elems(),
-            to.planes);
+            to.planes, enc->fp16);
         count_launch();
         break;
       }
@@ -781,7 +812,8 @@ int dad3d_encoder_forward(dad3d_encoder* enc, const float* images_d, int32_t B, 
         if (s.nsrc == 3) f2 = FuseSrc{view(s.in3), T(s.in3).H, T(s.in3).W, s.fw[2]};
         const long long total = static_cast<long long>(to.N) * to.H * to.W * (to.C / 8);
         bifpn_fuse_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
-            f0, f1, f2, s.nsrc, to.N, to.H, to.W, to.C, reinterpret_cast<uint16_t*>(to.ptr), to.plane_elems(), to.planes);
+            f0, f1, f2, s.nsrc, to.N, to.H, to.W, to.C, reinterpret_cast<uint16_t*>(to.ptr), to.plane_elems(), to.planes,
+            enc->fp16);
         count_launch();
         break;
       }
@@ -791,7 +823,7 @@ int dad3d_encoder_forward(dad3d_encoder* enc, const float* images_d, int32_t B, 
         const long long total = static_cast<long long>(to.N) * to.H * to.W * (to.C / 8);
         fusion_concat_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
             view(s.in), T(s.in).C, reinterpret_cast<const float*>(th.ptr), th.H, th.W, th.C, kHeat, kHeatCat, view(s.in3),
-            T(s.in3).C, to.N, to.H, to.W, reinterpret_cast<uint16_t*>(to.ptr), to.plane_elems(), to.planes);
+            T(s.in3).C, to.N, to.H, to.W, reinterpret_cast<uint16_t*>(to.ptr), to.plane_elems(), to.planes, enc->fp16);
         count_launch();
         break;
       }
@@ -800,7 +832,8 @@ int dad3d_encoder_forward(dad3d_encoder* enc, const float* images_d, int32_t B, 
         const TensorInfo& to = T(s.out);
         const int total = B * (ti.C / 8);
         gap_kernel<<<ceil_div(total, 128), 128, 0, stream>>>(view(s.in), B, ti.H * ti.W, ti.C,
-                                                             reinterpret_cast<uint16_t*>(to.ptr), to.plane_elems(), to.planes);
+                                                             reinterpret_cast<uint16_t*>(to.ptr), to.plane_elems(), to.planes,
+                                                             enc->fp16);
         count_launch();
         break;
       }
@@ -914,7 +947,7 @@ int dad3d_encoder_read_activation(dad3d_encoder* enc, const char* name, float* o
     if (t.f32) {
       DAD3D_CUDA_OK(cudaMemcpyAsync(out_d, t.ptr, n * 4, cudaMemcpyDeviceToDevice, stream));
     } else {
-      ActView v{reinterpret_cast<const uint16_t*>(t.ptr), t.plane_elems(), t.planes, t.C};
+      ActView v{reinterpret_cast<const uint16_t*>(t.ptr), t.plane_elems(), t.planes, t.C, enc->fp16};
       pieces_to_f32_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(v, static_cast<long long>(n), out_d);
       count_launch();
       DAD3D_CUDA_OK(cudaGetLastError());

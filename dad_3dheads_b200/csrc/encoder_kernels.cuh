@@ -10,23 +10,45 @@
 // (x = p0 + p1 + p2, see tile_gemm.cuh); plane p starts at base + p * plane_elems.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "tile_gemm.cuh"
 
 namespace dad3d {
 
 // ------------------------------------------------------------------------------------------------ piece helpers
+// Two 16-bit piece formats (GemmGeom::fmt16): bf16 (x = p0 + p1 + p2, 8 + 8 + 8 mantissa bits, fp32 exponent range) and
+// fp16 (x = hi + lo, 11 + 11 bits; |x| saturates at 65504 and the lo piece goes subnormal below |x| = 2^-3, leaving an
+// absolute representation error <= 2^-25).
 __device__ __forceinline__ uint16_t bf16_bits(float x) { return __bfloat16_as_ushort(__float2bfloat16_rn(x)); }
 __device__ __forceinline__ float bf16_to_f32(uint16_t b) { return __uint_as_float(static_cast<uint32_t>(b) << 16); }
 
-// split x into NP bf16 pieces (round-to-nearest each, remainder carried exactly in fp32)
-template <int NP>
-__device__ __forceinline__ void split_bf16(float x, uint16_t (&p)[NP]) {
-  float r = x;
-#pragma unroll
-  for (int i = 0; i < NP; ++i) {
-    p[i] = bf16_bits(r);
-    r -= bf16_to_f32(p[i]);
+// one piece of the pair (a, b): returns the packed 16-bit pieces (a low, b high) and leaves the exact remainders in a, b
+template <bool F16>
+__device__ __forceinline__ uint32_t split_pair(float& a, float& b) {
+  uint32_t w;
+  if constexpr (F16) {
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(b), "f"(a));
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w));
+    a -= f.x;
+    b -= f.y;
+  } else {
+    const uint16_t lo = bf16_bits(a), hi = bf16_bits(b);
+    a -= bf16_to_f32(lo);
+    b -= bf16_to_f32(hi);
+    w = static_cast<uint32_t>(lo) | (static_cast<uint32_t>(hi) << 16);
+  }
+  return w;
+}
+template <bool F16>
+__device__ __forceinline__ void add_pair(uint32_t w, float& a, float& b) {
+  if constexpr (F16) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w));
+    a += f.x;
+    b += f.y;
+  } else {
+    a += __uint_as_float(w << 16);
+    b += __uint_as_float(w & 0xffff0000u);
   }
 }
 
@@ -35,10 +57,14 @@ struct ActView {            // read-only view of a piece tensor
   long long plane;          // elements per plane
   int planes;
   int C;                    // channel stride (padded channel count)
+  int fp16;                 // piece format: 0 bf16, 1 fp16
 };
 __device__ __forceinline__ float act_load(const ActView& a, long long off) {
   float s = 0.f;
-  for (int p = a.planes - 1; p >= 0; --p) s += bf16_to_f32(__ldg(a.base + p * a.plane + off));   // small pieces first
+  for (int p = a.planes - 1; p >= 0; --p) {                                                    // small pieces first
+    const uint16_t h = __ldg(a.base + p * a.plane + off);
+    s += a.fp16 ? __half2float(__ushort_as_half(h)) : bf16_to_f32(h);
+  }
   return s;
 }
 // 8 consecutive channels (16 B per plane)
@@ -48,38 +74,37 @@ __device__ __forceinline__ void act_load8(const ActView& a, long long off, float
   for (int p = a.planes - 1; p >= 0; --p) {
     const uint4 q = __ldg(reinterpret_cast<const uint4*>(a.base + p * a.plane + off));
     const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+    if (a.fp16) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      v[2 * j] += __uint_as_float(w[j] << 16);
-      v[2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+      for (int j = 0; j < 4; ++j) add_pair<true>(w[j], v[2 * j], v[2 * j + 1]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) add_pair<false>(w[j], v[2 * j], v[2 * j + 1]);
     }
   }
 }
-__device__ __forceinline__ void act_store8(uint16_t* base, long long plane, int planes, long long off, const float (&v)[8]) {
+__device__ __forceinline__ void act_store8(uint16_t* base, long long plane, int planes, int fp16, long long off,
+                                           const float (&v)[8]) {
   float r[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) r[j] = v[j];
   for (int p = 0; p < planes; ++p) {
     uint32_t w[4];
+    if (fp16) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const uint16_t lo = bf16_bits(r[2 * j]), hi = bf16_bits(r[2 * j + 1]);
-      r[2 * j] -= bf16_to_f32(lo);
-      r[2 * j + 1] -= bf16_to_f32(hi);
-      w[j] = static_cast<uint32_t>(lo) | (static_cast<uint32_t>(hi) << 16);
+      for (int j = 0; j < 4; ++j) w[j] = split_pair<true>(r[2 * j], r[2 * j + 1]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) w[j] = split_pair<false>(r[2 * j], r[2 * j + 1]);
     }
     *reinterpret_cast<uint4*>(base + p * plane + off) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 
 // ------------------------------------------------------------------------------------------------ conv epilogue
-struct EpiConv {
-  static constexpr int kExtraSmemBytes = 0;
-  struct State {
-    float r[64];              // residual / gate operand of the current tile (this thread's row, this warp's columns)
-  };
-  struct Params {
+struct EpiConvParams {
     const float* bias;        // [Cout_pad] folded BN shift / conv bias
+    const float* scale;       // [Cout_pad] per-output-channel 2^-s that undoes the weight scaling (fp16 pieces only)
     int relu;
     int res_mode;             // 0 none, 1 add before ReLU (ResUnit), 2 multiply after bias (FusionLayer gate),
                               // 3 add a LOWER-RESOLUTION map nearest-up-sampled to the output grid (BiFPN top-down node)
@@ -91,7 +116,15 @@ struct EpiConv {
     int ld_out;
     float* out_f32;           // optional fp32 copy [pix][ld_f32]
     int ld_f32;
+};
+
+template <bool F16>
+struct EpiConvT {
+  static constexpr int kExtraSmemBytes = 0;
+  struct State {
+    float r[64];              // residual / gate operand of the current tile (this thread's row, this warp's columns)
   };
+  using Params = EpiConvParams;
   // fp32-only outputs (heat-map, MLP logits): direct vector stores of this thread's row
   static __device__ __forceinline__ void run_f32(const Params& ep, const EpiCtx& c) {
     int cb, ce;
@@ -110,7 +143,14 @@ struct EpiConv {
       for (int j = 0; j < 8; ++j) {
         if (tail16 && j >= 4) break;
         const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col) + j);
-        float4 o = make_float4(x[4 * j] + b.x, x[4 * j + 1] + b.y, x[4 * j + 2] + b.z, x[4 * j + 3] + b.w);
+        float4 o;
+        if constexpr (F16) {
+          const float4 sc = __ldg(reinterpret_cast<const float4*>(ep.scale + col) + j);
+          o = make_float4(fmaf(x[4 * j], sc.x, b.x), fmaf(x[4 * j + 1], sc.y, b.y), fmaf(x[4 * j + 2], sc.z, b.z),
+                          fmaf(x[4 * j + 3], sc.w, b.w));
+        } else {
+          o = make_float4(x[4 * j] + b.x, x[4 * j + 1] + b.y, x[4 * j + 2] + b.z, x[4 * j + 3] + b.w);
+        }
         if (ep.relu) {
           o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
         }
@@ -179,10 +219,7 @@ struct EpiConv {
           const uint4 v = *reinterpret_cast<const uint4*>(rowp + ((q4 ^ swz) << 4));
           const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            st.r[H * 32 + 8 * q4 + 2 * j] += __uint_as_float(w[j] << 16);
-            st.r[H * 32 + 8 * q4 + 2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
-          }
+          for (int j = 0; j < 4; ++j) add_pair<F16>(w[j], st.r[H * 32 + 8 * q4 + 2 * j], st.r[H * 32 + 8 * q4 + 2 * j + 1]);
         }
         __syncwarp();
       }
@@ -205,7 +242,13 @@ struct EpiConv {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col) + j);
-      x[4 * j] += b.x; x[4 * j + 1] += b.y; x[4 * j + 2] += b.z; x[4 * j + 3] += b.w;
+      if constexpr (F16) {
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(ep.scale + col) + j);
+        x[4 * j] = fmaf(x[4 * j], sc.x, b.x); x[4 * j + 1] = fmaf(x[4 * j + 1], sc.y, b.y);
+        x[4 * j + 2] = fmaf(x[4 * j + 2], sc.z, b.z); x[4 * j + 3] = fmaf(x[4 * j + 3], sc.w, b.w);
+      } else {
+        x[4 * j] += b.x; x[4 * j + 1] += b.y; x[4 * j + 2] += b.z; x[4 * j + 3] += b.w;
+      }
     }
     if (ep.res_mode == 1 || ep.res_mode == 3) {
 #pragma unroll
@@ -227,12 +270,7 @@ struct EpiConv {
       for (int q = 0; q < 4; ++q) {                   // 16-byte chunks of this row
         uint32_t w[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint16_t lo = bf16_bits(x[8 * q + 2 * j]), hi = bf16_bits(x[8 * q + 2 * j + 1]);
-          x[8 * q + 2 * j] -= bf16_to_f32(lo);
-          x[8 * q + 2 * j + 1] -= bf16_to_f32(hi);
-          w[j] = static_cast<uint32_t>(lo) | (static_cast<uint32_t>(hi) << 16);
-        }
+        for (int j = 0; j < 4; ++j) w[j] = split_pair<F16>(x[8 * q + 2 * j], x[8 * q + 2 * j + 1]);
         *reinterpret_cast<uint4*>(rowp + ((q ^ swz) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
       }
       ptx::fence_proxy_async_smem();
@@ -255,6 +293,8 @@ struct EpiConv {
     }
   }
 };
+using EpiConv = EpiConvT<false>;      // bf16 pieces
+using EpiConvH = EpiConvT<true>;      // fp16 hi/lo pieces, per-channel weight scale undone in the epilogue
 
 // ------------------------------------------------------------------------------------------------ stem
 // 7x7 stride-2 pad-3 conv, 3 -> 64 channels, BN folded, ReLU.  in: NCHW fp32 [B,3,H,W]; out: NHWC fp32 [B,H/2,W/2,64].
@@ -341,7 +381,7 @@ stem_conv_kernel(const float* __restrict__ img, const float* __restrict__ w /*[1
 
 // MaxPool2d(3, stride 2, pad 1) over NHWC fp32 [B,Hi,Wi,64] -> pieces [B,Hi/2,Wi/2,64].  thread = 8 channels of a pixel.
 __global__ void stem_pool_kernel(const float* __restrict__ in, int B, int Hi, int Wi, uint16_t* __restrict__ out,
-                                 long long out_plane, int planes) {
+                                 long long out_plane, int planes, int fp16) {
   const int Ho = Hi / 2, Wo = Wi / 2;
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long total = static_cast<long long>(B) * Ho * Wo * 8;
@@ -366,7 +406,7 @@ __global__ void stem_pool_kernel(const float* __restrict__ in, int B, int Hi, in
       m[4] = fmaxf(m[4], c.x); m[5] = fmaxf(m[5], c.y); m[6] = fmaxf(m[6], c.z); m[7] = fmaxf(m[7], c.w);
     }
   }
-  act_store8(out, out_plane, planes, pix * 64 + cg * 8, m);
+  act_store8(out, out_plane, planes, fp16, pix * 64 + cg * 8, m);
 }
 
 // ------------------------------------------------------------------------------------------------ BiFPN node input
@@ -378,7 +418,7 @@ struct FuseSrc {
   float w;
 };
 __global__ void bifpn_fuse_kernel(FuseSrc s0, FuseSrc s1, FuseSrc s2, int nsrc, int B, int H, int W, int C,
-                                  uint16_t* __restrict__ out, long long out_plane, int planes) {
+                                  uint16_t* __restrict__ out, long long out_plane, int planes, int fp16) {
   const int cgs = C / 8;
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long total = static_cast<long long>(B) * H * W * cgs;
@@ -404,7 +444,7 @@ __global__ void bifpn_fuse_kernel(FuseSrc s0, FuseSrc s1, FuseSrc s2, int nsrc, 
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] += s2.w * t[j];
   }
-  act_store8(out, out_plane, planes, pix * C + cg * 8, acc);
+  act_store8(out, out_plane, planes, fp16, pix * C + cg * 8, acc);
 }
 
 // ------------------------------------------------------------------------------------------------ FusionLayer input
@@ -412,7 +452,7 @@ __global__ void bifpn_fuse_kernel(FuseSrc s0, FuseSrc s1, FuseSrc s2, int nsrc, 
 // (flame_regression.py:33-41).  heat is fp32 NHWC [B,Hh,Wh,ldh]; channels >= n_heat of the middle block are zero.
 __global__ void fusion_concat_kernel(ActView x, int Cx, const float* __restrict__ heat, int Hh, int Wh, int ldh,
                                      int n_heat, int Ch_pad, ActView p5, int Cp, int B, int H, int W,
-                                     uint16_t* __restrict__ out, long long out_plane, int planes) {
+                                     uint16_t* __restrict__ out, long long out_plane, int planes, int fp16) {
   const int Ct = Cx + Ch_pad + Cp;
   const int cgs = Ct / 8;
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -453,12 +493,12 @@ __global__ void fusion_concat_kernel(ActView x, int Cx, const float* __restrict_
   } else {
     act_load8(p5, pix * Cp + (c - Cx - Ch_pad), v);
   }
-  act_store8(out, out_plane, planes, pix * Ct + c, v);
+  act_store8(out, out_plane, planes, fp16, pix * Ct + c, v);
 }
 
 // ------------------------------------------------------------------------------------------------ GAP
 // adaptive_avg_pool2d(., 1): [B,HW,C] -> [B,C] pieces.  thread = 8 channels of an image.
-__global__ void gap_kernel(ActView x, int B, int HW, int C, uint16_t* __restrict__ out, long long out_plane, int planes) {
+__global__ void gap_kernel(ActView x, int B, int HW, int C, uint16_t* __restrict__ out, long long out_plane, int planes, int fp16) {
   const int cgs = C / 8;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * cgs) return;
@@ -476,7 +516,7 @@ __global__ void gap_kernel(ActView x, int B, int HW, int C, uint16_t* __restrict
   const float inv = 1.f / static_cast<float>(HW);
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] *= inv;
-  act_store8(out, out_plane, planes, static_cast<long long>(b) * C + cg * 8, acc);
+  act_store8(out, out_plane, planes, fp16, static_cast<long long>(b) * C + cg * 8, acc);
 }
 
 // ------------------------------------------------------------------------------------------------ heads

@@ -24,7 +24,8 @@ BN_EPS_RESNET = 1e-5        # pytorchcv ConvBlock
 BN_EPS_BIFPN = 4e-5         # bifpn.py:36,66
 BIFPN_EPSILON = 1e-4        # bifpn.py:77
 
-PRECISION_PIECES = {"fp32": 3, "bf16x3": 3, "bf16x2": 2, "bf16": 1}
+PRECISION_PIECES = {"fp32": 3, "bf16x3": 3, "bf16x2": 2, "bf16": 1, "fp16x2": 2, "fp16": 1}
+PRECISION_FORMAT = {"fp32": 0, "bf16x3": 0, "bf16x2": 0, "bf16": 0, "fp16x2": 1, "fp16": 1}     # DAD3D_OPERAND_*
 
 
 def _bn_scale_shift(sd, p, eps):
@@ -131,7 +132,8 @@ class Dad3dEncoder:
     """``model(x: Tensor[B,3,256,256]) -> {OUTPUT_3DMM_PARAMS, OUTPUT_2D_LANDMARKS, OUTPUT_LANDMARKS_HEATMAP}`` on one GPU.
 
     precision: "fp32" (= "bf16x3": three-way bf16 split, 6 tensor-core products per tile, fp32-class accuracy -- the
-    parity mode), "bf16x2" (3 products, ~1e-5 relative) or "bf16" (plain bf16 operands, throughput mode).
+    parity mode), "fp16x2" (fp16 hi/lo, 3 products, 22-bit operands, per-channel scaled weights), "bf16x2" (3 products,
+    16-bit operands), "bf16" / "fp16" (one product, throughput modes).
     """
 
     def __init__(self, state_dict: Dict[str, Tensor], device: Optional[torch.device] = None, precision: str = "fp32",
@@ -144,7 +146,7 @@ class Dad3dEncoder:
             raise _lib.Dad3dError(f"Dad3dEncoder needs a cuda device, got {self.device}")
         self.precision = precision
         self.want_heatmap = want_heatmap
-        pieces = PRECISION_PIECES[precision]
+        pieces, fmt = PRECISION_PIECES[precision], PRECISION_FORMAT[precision]
         layers, fusion_w = fold_state_dict(state_dict)
         recs = (_ConvWeights * len(layers))()
         keep = []
@@ -156,7 +158,7 @@ class Dad3dEncoder:
             recs[i].cout, recs[i].R, recs[i].S, recs[i].cin = w.shape
         h = C.c_void_p()
         idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
-        _lib.check(self.lib.dad3d_encoder_create(C.byref(h), recs, len(layers), fusion_w.ctypes.data, pieces, idx),
+        _lib.check(self.lib.dad3d_encoder_create(C.byref(h), recs, len(layers), fusion_w.ctypes.data, pieces, fmt, idx),
                    "dad3d_encoder_create")
         self._h = h
         self._ws: Optional[Tensor] = None

@@ -100,7 +100,8 @@ DAD3D_API int dad3d_gather_landmarks_bary(const float* src_d, int32_t B, int32_t
  * Weights arrive BN-folded, one record per GEMM-able layer, fp32, laid out [cout][R][S][cin] (channels-last taps).
  * Layer names (the folding itself is host-side Python, dad_3dheads_b200/encoder.py, from the reference's state_dict):
  *   "stem" (7x7 3->64)                       encoder.model.init_block.conv
- *   "s{1..4}u{k}c{1,2,3}", "s{i}u1id"        encoder.model.stage{i}.unit{k}.body.conv{1,2,3} / .identity_conv
+ *   "s{1..4}u{k}c{1,2,3}"                    encoder.model.stage{i}.unit{k}.body.conv{1,2,3}; the first unit's c3 carries
+ *                                            the projection shortcut K-concatenated: [W3 | W_identity_conv], bias b3 + bid
  *   "lat3".."lat7"                           bifpn.p3 .. bifpn.p7
  *   "b{0,1}_{p4out,p5out,p6out,p7out}"       bifpn.bifpn.{0,1}.<node> (depthwise scale, pointwise, BN folded)
  *   "b{0,1}_{p6td,p5td,p4td,p3td}" and "..._u"   top-down nodes split in two: W*(w0 a) at the node's resolution and
@@ -110,8 +111,14 @@ DAD3D_API int dad3d_gather_landmarks_bary(const float* src_d, int32_t B, int32_t
  *   "mlp1" (2048 -> 3x512)  "mlp2" (block-diagonal 1536 -> 403|10|136)   {shape,pose,landmarks}.logit_image.{0,3}
  * bifpn_fusion_w_h: [2][20] = per BiFPN block the normalised fusion weights relu(w)/sum + 1e-4, w1 [2][4] then w2 [3][4]
  *   (bifpn.py:105-108).
- * pieces selects the arithmetic: 1 = plain bf16 operands (1 tensor-core product, throughput mode),
- *   2 = bf16 hi/lo (3 products, ~1e-5 relative), 3 = bf16 three-way split (6 products, fp32-class: the parity mode). */
+ * pieces / operand_format select the arithmetic (accumulation is always fp32):
+ *   DAD3D_OPERAND_BF16: 1 = plain bf16 operands (1 tensor-core product, throughput mode), 2 = bf16 hi/lo (3 products,
+ *     16-bit operand mantissa), 3 = bf16 three-way split (6 products, 24-bit operand mantissa: strict fp32 operands);
+ *   DAD3D_OPERAND_FP16: 2 = fp16 hi/lo (3 products, 22-bit operand mantissa; weights scaled per output channel by a power
+ *     of two that the epilogue undoes; activations saturate at +-65504 and carry an absolute representation error
+ *     <= 2^-25 below |x| = 2^-3), 1 = plain fp16 (11-bit, TF32-class). */
+#define DAD3D_OPERAND_BF16 0
+#define DAD3D_OPERAND_FP16 1
 typedef struct dad3d_conv_weights {
   const char* name;
   const float* weight_h;     /* [cout][R][S][cin] */
@@ -120,7 +127,7 @@ typedef struct dad3d_conv_weights {
 } dad3d_conv_weights;
 
 DAD3D_API int dad3d_encoder_create(dad3d_encoder** out, const dad3d_conv_weights* layers, int32_t n_layers,
-                                   const float* bifpn_fusion_w_h, int32_t pieces, int32_t device);
+                                   const float* bifpn_fusion_w_h, int32_t pieces, int32_t operand_format, int32_t device);
 DAD3D_API void dad3d_encoder_destroy(dad3d_encoder* enc);
 DAD3D_API int dad3d_encoder_num_layers(const dad3d_encoder* enc);
 DAD3D_API size_t dad3d_encoder_workspace_bytes(dad3d_encoder* enc, int32_t B);
