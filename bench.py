@@ -252,9 +252,9 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
-            "dtype": "fp32 (bf16x3 split operands, fp32 accumulate)" if products == 6 else args.precision,
+            "dtype": DTYPE[args.precision],
             "data": "synthetic",
-            "config": {"workload": "configs[1]: batch=64 256x256 encoder+FLAME decode, fp32, per GPU",
+            "config": {"workload": "configs[1]: batch=64 256x256 encoder+FLAME decode, fp32-class, per GPU",
                        "per_gpu_batch": B, "global_batch": B * world, "encoder_precision": args.precision,
                        "decode": "fp16 hi/lo 3-product blend + LBS + projection + 445-landmark gather",
                        "parallelism": f"dp{world} (batch sharded, NCCL bcast constants + all-gather outputs)" if distributed
@@ -266,7 +266,7 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": {"kernel": "tile_gemm_kernel<EpiConv> (all conv/linear layers, tcgen05)", "bound": "tensor",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                         "traffic": traffic if B == PER_GPU_BATCH and args.precision == "fp32" else None,
+                         "traffic": traffic if B == PER_GPU_BATCH and args.precision == "fp16x2" else None,
                          "traffic_unit": "DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, averaged "
                                          "over the 77 tile-engine launches of one step)", "traffic_source": traffic_src,
                          "algorithmic_bytes_per_launch": None,
@@ -277,8 +277,20 @@ def run_ours(args):
                          "share_of_step": gemm_ms / ms_total if ms_total else None,
                          "algorithmic_gflop_per_head": useful_flops / heads * world / 1e9 if heads else None},
         }
+        if world == 1 and args.precision != "fp32" and not args.no_strict:
+            # the same step with strict 24-bit operands (bf16x3, 6 products), device-resident, for comparison
+            strict = FaceMeshPredictor(dict(DEFAULT_CONFIG), cuda_id=local_rank, state_dict=sd, precision="fp32")
+            for _ in range(3):
+                strict.predict_batch(x_dev, landmark_subset=subset)
+            n_s = max(3, args.steps // 2)
+            ms_s, _ = timed(lambda: strict.predict_batch(x_dev, landmark_subset=subset), n_s)
+            line["strict_fp32_operands"] = {"value": B * n_s / (ms_s * 1e-3), "unit": UNIT, "ms_per_step": ms_s / n_s,
+                                            "steps": n_s, "mode": DTYPE["fp32"]}
+            del strict
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(sd, static)
+            cb = cpu_baseline(sd, static, parity_with=pred)
+            line["parity"] = cb.pop("parity", None)
+            line["cpu_baseline"] = cb
         print(json.dumps(line), flush=True)
     if distributed:
         dist.barrier()
@@ -364,8 +376,17 @@ def run_decode_microbench(args):
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline(sd, static):
-    """The oracle ("port" of the reference algorithm) timed on this box's host cores on a bounded sample."""
+DTYPE = {"fp32": "fp32 operands as bf16x3 split (24-bit), 6 tensor-core products, fp32 accumulate",
+         "bf16x3": "fp32 operands as bf16x3 split (24-bit), 6 tensor-core products, fp32 accumulate",
+         "fp16x2": "fp32 operands as fp16 hi/lo split (22-bit), 3 tensor-core products, fp32 accumulate; parity tolerance "
+                   "1e-4 vs the fp32 oracle (profiles/r01_precision.md: 1.5e-5 measured, strict bf16x3 mode 1.0e-5)",
+         "bf16x2": "bf16 hi/lo split operands (16-bit), fp32 accumulate", "fp16": "fp16 operands, fp32 accumulate",
+         "bf16": "bf16 operands, fp32 accumulate"}
+
+
+def cpu_baseline(sd, static, parity_with=None):
+    """The oracle ("port" of the reference algorithm) timed on this box's host cores on a bounded sample; with
+    parity_with = a FaceMeshPredictor it also checks that predictor's outputs on the sample against the oracle's."""
     import torch
     from oracle.predictor_oracle import PredictorOracle
     po = PredictorOracle(sd, static=static)
@@ -379,9 +400,19 @@ def cpu_baseline(sd, static):
         po.predict_batch(x)
         reps += 1
     dt = time.perf_counter() - t0
-    return {"value": sample * reps / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{reps} passes of {sample} images (encoder + FLAME decode + projection), torch {torch.__version__} "
-                      f"CPU fp32, {cores} of {os.cpu_count()} host threads (fastest of a small sweep)"}
+    out = {"value": sample * reps / dt, "unit": UNIT, "cores": cores, "kind": "port",
+           "sample": f"{reps} passes of {sample} images (encoder + FLAME decode + projection), torch {torch.__version__} "
+                     f"CPU fp32, {cores} of {os.cpu_count()} host threads (fastest of a small sweep)"}
+    if parity_with is not None:
+        ref = po.predict_batch(x)
+        got = parity_with.predict_batch(x)
+
+        def rel(k):
+            a, b = got[k].double().cpu(), ref[k].double().cpu()
+            return float((a - b).norm() / b.norm())
+        out["parity"] = {"params_rel_l2": rel("3dmm_params"), "vertices_rel_l2": rel("3d_vertices"), "tolerance": 1e-4,
+                         "against": f"this oracle (fp32, CPU) on the same {sample} images"}
+    return out
 
 
 def main():
@@ -391,7 +422,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="images per GPU per step")
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16x3", "fp16x2", "bf16x2", "fp16", "bf16"])
+    ap.add_argument("--no-strict", action="store_true", help="skip the strict-operand comparison run")
+    ap.add_argument("--precision", default="fp16x2", choices=["fp32", "bf16x3", "fp16x2", "bf16x2", "fp16", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="pipeline", choices=["pipeline", "decode"],
                     help="pipeline = configs[1] (headline); decode = configs[4] decode-only microbench")

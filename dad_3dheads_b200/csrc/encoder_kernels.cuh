@@ -1,6 +1,7 @@
 // Device code of the DAD-3DNet encoder (everything that is not the tcgen05 tile engine itself):
 //   EpiConv            fused conv epilogue: folded-BN bias, residual add / gate multiply, ReLU, split into bf16 pieces
-//   stem_conv_kernel   7x7/2 conv (Cin = 3) + folded BN + ReLU, fp32 CUDA cores, NCHW fp32 image -> NHWC fp32
+//   stem_conv_kernel   7x7/2 conv (Cin = 3) + folded BN + ReLU, fp32 CUDA cores, NCHW fp32 image -> NHWC fp32 (DAD3D_STEM_SIMT=1)
+//   stem_s2d_kernel    2x2 space-to-depth + piece split of the image: the stem runs on the tile engine as a 4x4 conv
 //   stem_pool_kernel   3x3/2 max-pool + split into pieces
 //   bifpn_fuse_kernel  fast-normalised weighted sum of 2-3 maps with nearest resampling (BiFPN node input)
 //   fusion_concat_kernel  [x | sigmoid(bilinear_align_corners(heatmap)) | p5] channel concat (FusionLayer input)
@@ -377,6 +378,43 @@ stem_conv_kernel(const float* __restrict__ img, const float* __restrict__ w /*[1
                          fmaxf(acc[p][7].x + bb3.z, 0.f), fmaxf(acc[p][7].y + bb3.w, 0.f));
     }
   }
+}
+
+// Space-to-depth of the input image for the tensor-core stem: NCHW fp32 [B,3,H,W] -> pieces [B, H/2, W/2 + kS2dPadW, 16],
+// channel c16 = (py * 2 + px) * 3 + ch for the 2x2 block's sub-pixel (py, px), channels 12..15 zero; kS2dPadL zero pixels on
+// the left and kS2dPadW - kS2dPadL on the right, so that a 4-pixel (64-element) window starting at padded x covers
+// s2d pixels x-2 .. x+1 without leaving the row: the 7x7/2 conv becomes a 4x4/1 conv over 12 channels whose 4 horizontal
+// taps are ONE contiguous 64-element K block (the A tensor map strides rows by 16 elements: overlapping windows).
+constexpr int kS2dPadL = 2;
+constexpr int kS2dPadW = 4;      // total horizontal padding (row pitch W/2 + 4)
+__global__ void stem_s2d_kernel(const float* __restrict__ img, int B, int H, int W, uint16_t* __restrict__ out,
+                                long long out_plane, int planes, int fp16) {
+  const int Hs = H / 2, Ws = W / 2, Wp = Ws + kS2dPadW;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(B) * Hs * Wp;
+  if (i >= total) return;
+  const int xp = static_cast<int>(i % Wp);
+  const int y = static_cast<int>((i / Wp) % Hs);
+  const long long b = i / (static_cast<long long>(Wp) * Hs);
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = 0.f;
+  const int x = xp - kS2dPadL;
+  if (x >= 0 && x < Ws) {
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+      for (int py = 0; py < 2; ++py) {
+        const float2 q = __ldg(reinterpret_cast<const float2*>(
+            img + ((b * 3 + ch) * H + (2 * y + py)) * static_cast<long long>(W) + 2 * x));
+        v[(py * 2 + 0) * 3 + ch] = q.x;
+        v[(py * 2 + 1) * 3 + ch] = q.y;
+      }
+  }
+  const float lo8[8] = {v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]};
+  const float hi8[8] = {v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15]};
+  act_store8(out, out_plane, planes, fp16, i * 16, lo8);
+  act_store8(out, out_plane, planes, fp16, i * 16 + 8, hi8);
 }
 
 // MaxPool2d(3, stride 2, pad 1) over NHWC fp32 [B,Hi,Wi,64] -> pieces [B,Hi/2,Wi/2,64].  thread = 8 channels of a pixel.
