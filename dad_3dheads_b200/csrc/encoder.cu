@@ -77,7 +77,7 @@ struct TensorInfo {
   long long plane_elems() const { return static_cast<long long>(N) * H * W * C; }
 };
 
-enum StepKind { kStemConv, kStemPool, kConv, kFuse, kConcat, kGap, kFinalize, kHeatExport };
+enum StepKind { kStemConv, kStemS2d, kStemPool, kConv, kFuse, kConcat, kGap, kFinalize, kHeatExport };
 
 struct Step {
   StepKind kind;
@@ -86,6 +86,8 @@ struct Step {
   // conv
   const ConvW* w = nullptr;
   int stride = 1, pad = 0, relu = 0, res_mode = 0, res_stride = 1;
+  int up2 = 0;                  // output stored 2x nearest-up-sampled ([N, 2Ho, 2Wo, C])
+  int stem = 0;                 // the stem as a GEMM: input = space-to-depth image, A map = overlapping 4-pixel windows
   GemmMaps maps;
   GemmGeom geom;
   EpiConv::Params epi;
@@ -119,6 +121,7 @@ struct dad3d_encoder {
   float bifpn_w[2][20];            // per block: w1 normalised [2][4] then w2 normalised [3][4]
   std::unique_ptr<Plan> plan;
   size_t ws_cache_B = 0, ws_cache_bytes = 0;
+  bool stem_simt = false;          // env DAD3D_STEM_SIMT=1: run the stem on the fp32 CUDA-core kernel instead of the tile engine
   bool use_pdl = false;            // programmatic dependent launch for the tile-engine kernels (env DAD3D_PDL=1 enables;
                                    // measured neutral on B200 at batch 64: 6689 vs 6764 heads/s, so off by default)
   bool debug_keep_all = false;     // disable buffer reuse so every activation can be read back after a forward
@@ -164,10 +167,10 @@ struct Builder {
     return it == enc->convs.end() ? nullptr : &it->second;
   }
   // conv / linear layer; returns the output tensor id (pieces) unless f32_only
-  // res_mode: 0 none, 1 residual add, 2 gate multiply, 3 up-sampled add, 4 second 1x1 source (stride res_stride) whose
-  // weights are K-concatenated behind the layer's own
+  // res_mode: 0 none, 1 residual add, 2 gate multiply, 4 second 1x1 source (stride res_stride) whose weights are
+  // K-concatenated behind the layer's own; up2: the output is written nearest-up-sampled by 2
   int conv(const std::string& name, int in, int stride, int pad, bool relu, int res = -1, int res_mode = 0,
-           bool f32_out = false, bool pieces_out = true, int* f32_id = nullptr, int res_stride = 1) {
+           bool f32_out = false, bool pieces_out = true, int* f32_id = nullptr, int res_stride = 1, bool up2 = false) {
     const ConvW* w = W(name);
     const TensorInfo ti = plan->tensors[in];
     const int Ho = (ti.H + 2 * pad - w->R) / stride + 1;
@@ -183,7 +186,8 @@ struct Builder {
     s.res = res;
     s.res_mode = res_mode;
     s.res_stride = res_stride;
-    s.out = pieces_out ? tensor(ti.N, Ho, Wo, w->cout_pad) : -1;
+    s.up2 = up2 ? 1 : 0;
+    s.out = pieces_out ? tensor(ti.N, up2 ? 2 * Ho : Ho, up2 ? 2 * Wo : Wo, w->cout_pad) : -1;
     s.out_f32 = f32_out ? tensor(ti.N, Ho, Wo, w->cout_pad, true) : -1;
     if (s.out >= 0) plan->tensors[s.out].name = name;
     if (s.out_f32 >= 0) plan->tensors[s.out_f32].name = name + (pieces_out ? ".f32" : "");
@@ -208,8 +212,26 @@ int build_graph(Builder& b) {
   Plan* plan = b.plan;
   // ---- stem: conv7x7/2 + BN + ReLU (fp32 SIMT) -> maxpool 3x3/2 -> pieces [B,64,64,64]
   const int t_stem = b.tensor(B, kImg / 2, kImg / 2, 64, true);
-  {
+  if (b.enc->stem_simt) {
     Step s; s.kind = kStemConv; s.out_f32 = t_stem; std::memset(&s.maps, 0, sizeof(s.maps));
+    b.push(s);
+  } else {
+    // tensor-core stem: 2x2 space-to-depth (+ piece split) of the image, then a 4x4/1 conv over 12 channels whose four
+    // horizontal taps form one 64-element K block (4 k-blocks, K = 256 of which 147 are non-zero)
+    const int t_s2d = b.tensor(B, kImg / 2, kImg / 2 + kS2dPadW, 16);
+    plan->tensors[t_s2d].name = "s2d";
+    {
+      Step s; s.kind = kStemS2d; s.out = t_s2d; std::memset(&s.maps, 0, sizeof(s.maps));
+      b.push(s);
+    }
+    Step s;
+    std::memset(&s.maps, 0, sizeof(s.maps));
+    s.kind = kConv;
+    s.in = t_s2d;
+    s.w = b.W("stem");
+    s.stem = 1;
+    s.relu = 1;
+    s.out_f32 = t_stem;
     b.push(s);
   }
   plan->tensors[t_stem].name = "stem_conv";
@@ -270,10 +292,11 @@ int build_graph(Builder& b) {
     const int p3x = feat[0], p4x = feat[1], p5x = feat[2], p6x = feat[3], p7x = feat[4];
     const int p7td = p7x;
     // top-down nodes (bifpn.py:111-114): node(w0*a + w1*up(b)) = relu(W0 a + up(W1 b) + shift); the fusion scalars are
-    // folded into the two weight sets on the host, the low-resolution product is added in the epilogue (res_mode 3)
+    // folded into the two weight sets on the host.  The low-resolution product is stored nearest-up-sampled (every pixel
+    // to its 2x2 block) and enters the node's GEMM through identity columns on the K axis, like a ResUnit residual.
     auto td_node = [&](const std::string& name, int a, int lower) {
-      const int u = b.conv(name + "_u", lower, 1, 0, false);
-      return b.conv(name, a, 1, 0, true, u, 3);
+      const int u = b.conv(name + "_u", lower, 1, 0, false, -1, 0, false, true, nullptr, 1, /*up2=*/true);
+      return b.conv(name, a, 1, 0, true, u, 1);
     };
     const int p6td = td_node(p + "p6td", p6x, p7td);
     const int p5td = td_node(p + "p5td", p5x, p6td);
@@ -396,13 +419,13 @@ int make_plan(dad3d_encoder* enc, int B, void* ws, size_t ws_bytes, bool layout_
     const ConvW* w = s.w;
     const bool src2 = s.res >= 0 && s.res_mode == 4;
     const int cin2 = src2 ? plan->tensors[s.res].C : 0;
-    if (ti.C + cin2 != w->cin_pad) {
+    if (!s.stem && ti.C + cin2 != w->cin_pad) {
       set_error("layer " + w->name + ": input has " + std::to_string(ti.C) + "+" + std::to_string(cin2) +
                 " channels, weights expect " + std::to_string(w->cin_pad));
       return DAD3D_ERR_INVALID;
     }
-    const int Ho = (ti.H + 2 * s.pad - w->R) / s.stride + 1;
-    const int Wo = (ti.W + 2 * s.pad - w->S) / s.stride + 1;
+    const int Ho = s.stem ? ti.H : (ti.H + 2 * s.pad - w->R) / s.stride + 1;
+    const int Wo = s.stem ? ti.W - kS2dPadW : (ti.W + 2 * s.pad - w->S) / s.stride + 1;
     GemmGeom& g = s.geom;
     std::memset(&g, 0, sizeof(g));
     pick_tile(Wo, Ho, &g.tw, &g.th, &g.tn);
@@ -413,6 +436,7 @@ int make_plan(dad3d_encoder* enc, int B, void* ws, size_t ws_bytes, bool layout_
     g.stride = s.stride;
     g.R = w->R; g.S = w->S; g.pad_h = s.pad; g.pad_w = s.pad;
     g.cin_blocks = ti.C / kBlockK;                    // main source; a second source adds res_kb blocks below
+    if (s.stem) { g.cin_blocks = 1; g.pad_h = 2; g.pad_w = 0; }   // 4 vertical taps x one 64-element window
     g.cl_m = 1; g.cl_n = 1;
     const bool res_in_k = s.res >= 0 && s.res_mode == 1 && w->has_identity;
     // few row tiles (small maps / small batch): halve the tile width so that twice as many CTAs share the work
@@ -442,8 +466,10 @@ int make_plan(dad3d_encoder* enc, int B, void* ws, size_t ws_bytes, bool layout_
     g.stages = gemm_max_stages(g);
     if (g.stages < 2) { set_error("layer " + w->name + ": pipeline does not fit shared memory"); return DAD3D_ERR_INVALID; }
     for (int p = 0; p < enc->P; ++p) {
-      const uint64_t dims[4] = {static_cast<uint64_t>(ti.C), static_cast<uint64_t>(ti.W), static_cast<uint64_t>(ti.H),
-                                static_cast<uint64_t>(ti.N)};
+      // stem: row x of the A operand is the 64-element window that starts at padded s2d pixel x (dim 1 advances by one
+      // 16-channel pixel = 32 bytes while the window is 128 bytes long: consecutive rows overlap)
+      const uint64_t dims[4] = {static_cast<uint64_t>(s.stem ? kBlockK : ti.C), static_cast<uint64_t>(s.stem ? Wo : ti.W),
+                                static_cast<uint64_t>(ti.H), static_cast<uint64_t>(ti.N)};
       const uint64_t strides[3] = {static_cast<uint64_t>(ti.C) * 2, static_cast<uint64_t>(ti.W) * ti.C * 2,
                                    static_cast<uint64_t>(ti.H) * ti.W * ti.C * 2};
       const uint32_t box[4] = {kBlockK, static_cast<uint32_t>(g.tw * s.stride), static_cast<uint32_t>(g.th * s.stride),
@@ -475,10 +501,7 @@ int make_plan(dad3d_encoder* enc, int B, void* ws, size_t ws_bytes, bool layout_
     ep.relu = s.relu;
     ep.res_mode = (res_in_k || src2) ? 0 : s.res_mode;
     ep.res = view(s.res);
-    if (s.res >= 0) {
-      ep.res_h = plan->tensors[s.res].H;
-      ep.res_w = plan->tensors[s.res].W;
-    }
+    ep.up2 = s.up2;
     if (s.res >= 0 && !src2 && plan->tensors[s.res].C != w->cout_pad) {
       set_error("layer " + w->name + ": residual channel mismatch");
       return DAD3D_ERR_INVALID;
@@ -499,13 +522,24 @@ int make_plan(dad3d_encoder* enc, int B, void* ws, size_t ws_bytes, bool layout_
       const int bh = std::min(g.th, 32 / bw);
       const int bn = 32 / (bw * bh);
       for (int p = 0; p < to.planes; ++p) {
+        uint16_t* basep = reinterpret_cast<uint16_t*>(to.ptr) + static_cast<size_t>(p) * to.plane_elems();
+        if (s.up2) {
+          // [N, 2Ho, 2Wo, C] seen as (C, b, j, a, n*Ho + i): pixel (2i + a, 2j + b); a box with b = a = 1 addresses the
+          // sub-grid of one parity, so the same staging tile is stored four times
+          const uint64_t C2 = static_cast<uint64_t>(to.C) * 2;
+          const uint64_t dims[5] = {static_cast<uint64_t>(to.C), 2, static_cast<uint64_t>(Wo), 2,
+                                    static_cast<uint64_t>(to.N) * Ho};
+          const uint64_t strides[4] = {C2, 2 * C2, static_cast<uint64_t>(to.W) * C2, 2 * static_cast<uint64_t>(to.W) * C2};
+          const uint32_t box[5] = {static_cast<uint32_t>(nc), 1, static_cast<uint32_t>(bw), 1, static_cast<uint32_t>(bh * bn)};
+          if (!make_tmap_16bit(&s.maps.c[p], basep, 5, dims, strides, box, nullptr, nc * 2)) return DAD3D_ERR_CUDA;
+          continue;
+        }
         const uint64_t dims[4] = {static_cast<uint64_t>(to.C), static_cast<uint64_t>(to.W), static_cast<uint64_t>(to.H),
                                   static_cast<uint64_t>(to.N)};
         const uint64_t strides[3] = {static_cast<uint64_t>(to.C) * 2, static_cast<uint64_t>(to.W) * to.C * 2,
                                      static_cast<uint64_t>(to.H) * to.W * to.C * 2};
         const uint32_t box[4] = {static_cast<uint32_t>(nc), static_cast<uint32_t>(bw), static_cast<uint32_t>(bh),
                                  static_cast<uint32_t>(bn)};
-        uint16_t* basep = reinterpret_cast<uint16_t*>(to.ptr) + static_cast<size_t>(p) * to.plane_elems();
         if (!make_tmap_16bit(&s.maps.c[p], basep, 4, dims, strides, box, nullptr, nc * 2)) return DAD3D_ERR_CUDA;
       }
     }
@@ -525,6 +559,7 @@ double conv_useful_flops(const Step& s) {
   double cin = w->cin, cout = w->cout;
   if (w->name == "fusion") cin -= 60;                       // zero columns that pad the heat-map slot
   if (w->name == "mlp2") cin /= 3.0;                        // block-diagonal: each output sees one 512-wide block
+  if (w->name == "stem") return 2.0 * g.Nimg * g.Ho * g.Wo * cout * 147.0;   // the 7x7x3 taps (the rest of K = 256 is zero)
   return 2.0 * g.Nimg * g.Ho * g.Wo * cout * cin * w->R * w->S;
 }
 
@@ -611,11 +646,14 @@ int dad3d_encoder_create(dad3d_encoder** out, const dad3d_conv_weights* layers, 
   {
     const char* e = std::getenv("DAD3D_PDL");
     enc->use_pdl = (e && e[0] == '1');
+    const char* e2 = std::getenv("DAD3D_STEM_SIMT");
+    enc->stem_simt = (e2 && e2[0] == '1');
   }
 
   auto fail = [&](int code) { dad3d_encoder_destroy(enc.release()); return code; };
+  std::vector<float> stem_w4;                      // the stem's 7x7/2 filter re-expressed as 4x4/1 over the 2x2 space-to-depth image
   for (int li = 0; li < n_layers; ++li) {
-    const dad3d_conv_weights& L = layers[li];
+    dad3d_conv_weights L = layers[li];
     if (!L.name || !L.weight_h || !L.bias_h || L.cout <= 0 || L.cin <= 0 || L.R <= 0 || L.S <= 0) {
       set_error("invalid layer record " + std::to_string(li));
       return fail(DAD3D_ERR_INVALID);
@@ -635,7 +673,22 @@ int dad3d_encoder_create(dad3d_encoder** out, const dad3d_conv_weights* layers, 
         set_error("stem upload failed");
         return fail(DAD3D_ERR_CUDA);
       }
-      continue;
+      // tensor-core stem: K index = r * 64 + dx * 16 + (py * 2 + px) * 3 + ch for block row/column offsets r, dx in 0..3
+      // (s2d block oy - 2 + r, ox - 2 + dx); the original tap is ky = 2 r + py - 1, kx = 2 dx + px - 1 (zero outside 0..6)
+      stem_w4.assign(static_cast<size_t>(64) * 4 * 64, 0.f);
+      for (int o = 0; o < 64; ++o)
+        for (int r = 0; r < 4; ++r)
+          for (int dx = 0; dx < 4; ++dx)
+            for (int py = 0; py < 2; ++py)
+              for (int px = 0; px < 2; ++px) {
+                const int ky = 2 * r + py - 1, kx = 2 * dx + px - 1;
+                if (ky < 0 || ky > 6 || kx < 0 || kx > 6) continue;
+                for (int c = 0; c < 3; ++c)
+                  stem_w4[(static_cast<size_t>(o) * 4 + r) * 64 + dx * 16 + (py * 2 + px) * 3 + c] =
+                      L.weight_h[((static_cast<size_t>(o) * 7 + ky) * 7 + kx) * 3 + c];
+              }
+      L.weight_h = stem_w4.data();
+      L.cin = 64; L.R = 4; L.S = 1;                 // falls through to the generic packing below
     }
     ConvW cw;
     cw.name = name;
@@ -645,8 +698,9 @@ int dad3d_encoder_create(dad3d_encoder** out, const dad3d_conv_weights* layers, 
     cw.cin_pad = ceil_div(L.cin, kBlockK) * kBlockK;
     // the last 1x1 of a ResUnit ("...c3") gets identity columns appended to its K axis: [W | I] * [a ; residual]
     // (the first unit's c3 carries the projection-shortcut weights in its K axis instead and needs no identity)
-    cw.has_identity = name.size() > 4 && name.compare(name.size() - 2, 2, "c3") == 0 && L.R == 1 && L.S == 1 &&
-                      name.compare(name.size() - 4, 4, "u1c3") != 0;
+    cw.has_identity = name.size() > 4 && L.R == 1 && L.S == 1 &&
+                      ((name.compare(name.size() - 2, 2, "c3") == 0 && name.compare(name.size() - 4, 4, "u1c3") != 0) ||
+                       name.compare(name.size() - 2, 2, "td") == 0);      // BiFPN top-down nodes add the up-sampled branch
     const size_t ktot_main = static_cast<size_t>(L.R) * L.S * cw.cin_pad;
     const size_t ktot = ktot_main + (cw.has_identity ? cw.cout_pad : 0);
     const size_t plane = static_cast<size_t>(cw.cout_pad) * ktot;
@@ -786,6 +840,14 @@ int dad3d_encoder_forward(dad3d_encoder* enc, const float* images_d, int32_t B, 
         }
         stem_conv_kernel<<<grid, 256, kStemSmemBytes, stream>>>(images_d, enc->d_stem_w, enc->d_stem_b, kImg, kImg,
                                                    reinterpret_cast<float*>(to.ptr));
+        count_launch();
+        break;
+      }
+      case kStemS2d: {
+        const TensorInfo& to = T(s.out);
+        const long long total = static_cast<long long>(B) * to.H * to.W;
+        stem_s2d_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+            images_d, B, kImg, kImg, reinterpret_cast<uint16_t*>(to.ptr), to.plane_elems(), to.planes, enc->fp16);
         count_launch();
         break;
       }
@@ -958,6 +1020,6 @@ int dad3d_encoder_read_activation(dad3d_encoder* enc, const char* name, float* o
   return DAD3D_ERR_INVALID;
 }
 
-int dad3d_encoder_num_layers(const dad3d_encoder* enc) { return enc ? static_cast<int>(enc->convs.size()) + 1 : 0; }
+int dad3d_encoder_num_layers(const dad3d_encoder* enc) { return enc ? static_cast<int>(enc->convs.size()) : 0; }   // "stem" is in convs too
 
 }  // extern "C"

@@ -107,10 +107,10 @@ struct EpiConvParams {
     const float* bias;        // [Cout_pad] folded BN shift / conv bias
     const float* scale;       // [Cout_pad] per-output-channel 2^-s that undoes the weight scaling (fp16 pieces only)
     int relu;
-    int res_mode;             // 0 none, 1 add before ReLU (ResUnit), 2 multiply after bias (FusionLayer gate),
-                              // 3 add a LOWER-RESOLUTION map nearest-up-sampled to the output grid (BiFPN top-down node)
-    ActView res;              // modes 1/2: same pixel indexing as the output; mode 3: [N, res_h, res_w, C]
-    int res_h, res_w;         // mode 3 source extents (src = floor(dst * in / out), F.interpolate nearest)
+    int res_mode;             // 0 none, 1 add before ReLU, 2 multiply after bias (FusionLayer gate); same pixel indexing
+    ActView res;              // as the output.  (ResUnit / BiFPN residual adds normally ride the K axis instead.)
+    int up2;                  // store every output pixel to the 2x2 block it covers in a [N, 2H, 2W, C] tensor (nearest
+                              // up-sampling fused into the store: maps.c are 5-D parity views, see make_plan)
     uint16_t* out;            // piece planes [planes][pix][ld_out]; may be null when only out_f32 is wanted
     long long out_plane;
     int out_planes;
@@ -181,11 +181,7 @@ struct EpiConvT {
     //    a single memory round trip instead of one per plane
     uint4 q[3][4];
     const int planes = ep.res.planes;
-    long long rpix = c.pix;                            // this lane's row in the residual tensor
-    if (ep.res_mode == 3) {
-      const int sh = (c.h * ep.res_h) / c.g->Ho, sw = (c.w * ep.res_w) / c.g->Wo;
-      rpix = (static_cast<long long>(c.n) * ep.res_h + sh) * ep.res_w + sw;
-    }
+    const long long rpix = c.pix;                      // this lane's row in the residual tensor
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
       const int idx = it * 32 + c.lane;
@@ -251,7 +247,7 @@ struct EpiConvT {
         x[4 * j] += b.x; x[4 * j + 1] += b.y; x[4 * j + 2] += b.z; x[4 * j + 3] += b.w;
       }
     }
-    if (ep.res_mode == 1 || ep.res_mode == 3) {
+    if (ep.res_mode == 1) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) x[j] += st.r[H * 32 + j];
     } else if (ep.res_mode == 2) {
@@ -277,7 +273,13 @@ struct EpiConvT {
       ptx::fence_proxy_async_smem();
       __syncwarp();
       if (c.lane == 0) {
-        ptx::tma_store_4d(&c.maps->c[p], c.stage, col, c.bw0, c.bh0, c.bn0);
+        if (ep.up2) {
+          const int row0 = c.bn0 * c.g->Ho + c.bh0;   // merged (image, row) coordinate of the 5-D parity view
+#pragma unroll
+          for (int ab = 0; ab < 4; ++ab) ptx::tma_store_5d(&c.maps->c[p], c.stage, col, ab & 1, c.bw0, ab >> 1, row0);
+        } else {
+          ptx::tma_store_4d(&c.maps->c[p], c.stage, col, c.bw0, c.bh0, c.bn0);
+        }
         ptx::bulk_commit();
       }
     }

@@ -59,11 +59,15 @@ def run_folded(x: torch.Tensor, layers, fusion_w: np.ndarray, dtype=torch.float6
         p3x, p4x, p5x, p6x, p7x = feat
         p = f"b{li}_"
         p7td = p7x
-        # top-down nodes: fusion weights are folded into the two weight sets; the low-res product is up-sampled and added
-        p6td = conv(p + "p6td", p6x, relu=True, res=near(conv(p + "p6td_u", p7td), p6x))
-        p5td = conv(p + "p5td", p5x, relu=True, res=near(conv(p + "p5td_u", p6td), p5x))
-        p4td = conv(p + "p4td", p4x, relu=True, res=near(conv(p + "p4td_u", p5td), p4x))
-        p3td = conv(p + "p3td", p3x, relu=True, res=near(conv(p + "p3td_u", p4td), p3x))
+        # top-down nodes: fusion weights are folded into the two weight sets; the low-res product is stored nearest-up-sampled
+        # (that is the activation the engine keeps under the "_u" name) and added
+        def up(name, low, ref):
+            acts[name] = near(conv(name, low), ref)
+            return acts[name]
+        p6td = conv(p + "p6td", p6x, relu=True, res=up(p + "p6td_u", p7td, p6x))
+        p5td = conv(p + "p5td", p5x, relu=True, res=up(p + "p5td_u", p6td, p5x))
+        p4td = conv(p + "p4td", p4x, relu=True, res=up(p + "p4td_u", p5td, p4x))
+        p3td = conv(p + "p3td", p3x, relu=True, res=up(p + "p3td_u", p4td, p3x))
         p4o = conv(p + "p4out", w2[0, 0] * p4x + w2[1, 0] * p4td + w2[2, 0] * near(p3td, p4x), relu=True)
         p5o = conv(p + "p5out", w2[0, 1] * p5x + w2[1, 1] * p5td + w2[2, 1] * near(p4o, p5x), relu=True)
         p6o = conv(p + "p6out", w2[0, 2] * p6x + w2[1, 2] * p6td + w2[2, 2] * near(p5o, p6x), relu=True)
