@@ -892,8 +892,7 @@ int dad3d_encoder_forward(dad3d_encoder* enc, const float* images_d, int32_t B, 
       case kGap: {
         const TensorInfo& ti = T(s.in);
         const TensorInfo& to = T(s.out);
-        const int total = B * (ti.C / 8);
-        gap_kernel<<<ceil_div(total, 128), 128, 0, stream>>>(view(s.in), B, ti.H * ti.W, ti.C,
+        gap_kernel<<<B * (ti.C / 64), 256, 0, stream>>>(view(s.in), B, ti.H * ti.W, ti.C,
                                                              reinterpret_cast<uint16_t*>(to.ptr), to.plane_elems(), to.planes,
                                                              enc->fp16);
         count_launch();

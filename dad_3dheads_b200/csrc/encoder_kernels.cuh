@@ -68,19 +68,26 @@ __device__ __forceinline__ float act_load(const ActView& a, long long off) {
   }
   return s;
 }
-// 8 consecutive channels (16 B per plane)
+// 8 consecutive channels (16 B per plane); every plane's load is issued before the first one is consumed
 __device__ __forceinline__ void act_load8(const ActView& a, long long off, float (&v)[8]) {
+  uint4 q[3];
+#pragma unroll
+  for (int p = 0; p < 3; ++p)
+    if (p < a.planes) q[p] = __ldg(reinterpret_cast<const uint4*>(a.base + p * a.plane + off));
 #pragma unroll
   for (int j = 0; j < 8; ++j) v[j] = 0.f;
-  for (int p = a.planes - 1; p >= 0; --p) {
-    const uint4 q = __ldg(reinterpret_cast<const uint4*>(a.base + p * a.plane + off));
-    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-    if (a.fp16) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) add_pair<true>(w[j], v[2 * j], v[2 * j + 1]);
-    } else {
+  for (int pp = 0; pp < 3; ++pp) {
+    const int p = 2 - pp;                                        // small pieces first
+    if (p < a.planes) {
+      const uint32_t w[4] = {q[p].x, q[p].y, q[p].z, q[p].w};
+      if (a.fp16) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) add_pair<false>(w[j], v[2 * j], v[2 * j + 1]);
+        for (int j = 0; j < 4; ++j) add_pair<true>(w[j], v[2 * j], v[2 * j + 1]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) add_pair<false>(w[j], v[2 * j], v[2 * j + 1]);
+      }
     }
   }
 }
@@ -468,21 +475,21 @@ __global__ void bifpn_fuse_kernel(FuseSrc s0, FuseSrc s1, FuseSrc s2, int nsrc, 
   const int x = static_cast<int>(pix % W);
   const int y = static_cast<int>((pix / W) % H);
   const long long b = pix / (static_cast<long long>(W) * H);
-  float acc[8], t[8];
-  act_load8(s0.v, pix * C + cg * 8, t);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = s0.w * t[j];
+  float acc[8], t0[8], t1[8], t2[8];
+  act_load8(s0.v, pix * C + cg * 8, t0);
   {
     const int sy = (y * s1.H) / H, sx = (x * s1.W) / W;
-    act_load8(s1.v, ((b * s1.H + sy) * s1.W + sx) * C + cg * 8, t);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] += s1.w * t[j];
+    act_load8(s1.v, ((b * s1.H + sy) * s1.W + sx) * C + cg * 8, t1);
   }
   if (nsrc == 3) {
     const int sy = (y * s2.H) / H, sx = (x * s2.W) / W;
-    act_load8(s2.v, ((b * s2.H + sy) * s2.W + sx) * C + cg * 8, t);
+    act_load8(s2.v, ((b * s2.H + sy) * s2.W + sx) * C + cg * 8, t2);
+  }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] += s2.w * t[j];
+  for (int j = 0; j < 8; ++j) {
+    acc[j] = s0.w * t0[j];
+    acc[j] += s1.w * t1[j];
+    if (nsrc == 3) acc[j] += s2.w * t2[j];
   }
   act_store8(out, out_plane, planes, fp16, pix * C + cg * 8, acc);
 }
@@ -538,25 +545,41 @@ __global__ void fusion_concat_kernel(ActView x, int Cx, const float* __restrict_
 
 // ------------------------------------------------------------------------------------------------ GAP
 // adaptive_avg_pool2d(., 1): [B,HW,C] -> [B,C] pieces.  thread = 8 channels of an image.
-__global__ void gap_kernel(ActView x, int B, int HW, int C, uint16_t* __restrict__ out, long long out_plane, int planes, int fp16) {
+// block = one image x 8 channel groups (64 channels); thread = (pixel slice 0..31, channel group): pixels slice, slice+32, ...
+constexpr int kGapSlices = 32;
+__global__ void __launch_bounds__(256)
+gap_kernel(ActView x, int B, int HW, int C, uint16_t* __restrict__ out, long long out_plane, int planes, int fp16) {
+  __shared__ float red[kGapSlices][8][9];
   const int cgs = C / 8;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B * cgs) return;
-  const int cg = i % cgs;
-  const int b = i / cgs;
+  const int blocks_per_img = cgs / 8;
+  const int b = blockIdx.x / blocks_per_img;
+  const int cg = (blockIdx.x % blocks_per_img) * 8 + (threadIdx.x & 7);
+  const int slice = threadIdx.x >> 3;
   float acc[8], t[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-#pragma unroll 4
-  for (int p = 0; p < HW; ++p) {                    // (unrolled: several pixels' loads in flight per thread)
+  for (int p = slice; p < HW; p += kGapSlices) {
     act_load8(x, (static_cast<long long>(b) * HW + p) * C + cg * 8, t);
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] += t[j];
   }
-  const float inv = 1.f / static_cast<float>(HW);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] *= inv;
-  act_store8(out, out_plane, planes, fp16, static_cast<long long>(b) * C + cg * 8, acc);
+  for (int j = 0; j < 8; ++j) red[slice][threadIdx.x & 7][j] = acc[j];
+  __syncthreads();
+  if (threadIdx.x < 64) {                           // thread = (channel group, channel): fixed-order sum over the slices
+    const int g = threadIdx.x >> 3, j = threadIdx.x & 7;
+    float sum = 0.f;
+    for (int sl = 0; sl < kGapSlices; ++sl) sum += red[sl][g][j];
+    red[0][g][j] = sum / static_cast<float>(HW);
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = red[0][threadIdx.x][j];
+    const int cgo = (blockIdx.x % blocks_per_img) * 8 + threadIdx.x;
+    act_store8(out, out_plane, planes, fp16, static_cast<long long>(b) * C + cgo * 8, o);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ heads
