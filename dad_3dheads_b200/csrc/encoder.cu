@@ -122,6 +122,7 @@ struct dad3d_encoder {
   std::unique_ptr<Plan> plan;
   size_t ws_cache_B = 0, ws_cache_bytes = 0;
   bool stem_simt = false;          // env DAD3D_STEM_SIMT=1: run the stem on the fp32 CUDA-core kernel instead of the tile engine
+  bool use_pair = false;           // env DAD3D_PAIR=1: cta_group::2 CTA pairs for the large 128-wide layers
   bool use_pdl = false;            // programmatic dependent launch for the tile-engine kernels (env DAD3D_PDL=1 enables;
                                    // measured neutral on B200 at batch 64: 6689 vs 6764 heads/s, so off by default)
   bool debug_keep_all = false;     // disable buffer reuse so every activation can be read back after a forward
@@ -463,6 +464,10 @@ int make_plan(dad3d_encoder* enc, int B, void* ws, size_t ws_bytes, bool layout_
       g.res_kind = 1;
       g.res_stride = s.res_stride;
     }
+    // CTA pairs (cta_group::2): each CTA of a pair loads only half of the B tile; worth it when every SM pair has work
+    const bool pair = enc->use_pair && block_n == 128 && w->has_b64 &&
+                      ((m_tiles + 1) / 2) * g.n_tiles >= enc->num_sms / 2;
+    g.pair = pair ? 1 : 0;
     g.stages = gemm_max_stages(g);
     if (g.stages < 2) { set_error("layer " + w->name + ": pipeline does not fit shared memory"); return DAD3D_ERR_INVALID; }
     for (int p = 0; p < enc->P; ++p) {
@@ -477,7 +482,7 @@ int make_plan(dad3d_encoder* enc, int B, void* ws, size_t ws_bytes, bool layout_
       const uint32_t es[4] = {1, static_cast<uint32_t>(s.stride), static_cast<uint32_t>(s.stride), 1};
       const uint16_t* basep = reinterpret_cast<const uint16_t*>(ti.ptr) + static_cast<size_t>(p) * ti.plane_elems();
       if (!make_tmap_16bit(&s.maps.a[p], basep, 4, dims, strides, box, es)) return DAD3D_ERR_CUDA;
-      s.maps.b[p] = narrow ? w->map_b64[p] : w->map_b[p];
+      s.maps.b[p] = (narrow || pair) ? w->map_b64[p] : w->map_b[p];    // pair: each CTA loads a 64-row half of the B tile
     }
     if (res_in_k || src2) {
       const TensorInfo& tr = plan->tensors[s.res];
@@ -571,8 +576,9 @@ int launch_conv(dad3d_encoder* enc, const Step& s, cudaStream_t stream) {
     configured = true;
   }
   const GemmGeom& g = s.geom;
-  const int total = g.tiles_w * g.tiles_h * g.tiles_n * g.n_tiles;
-  const int grid = std::min(total, enc->num_sms);
+  const int m_tiles_total = g.tiles_w * g.tiles_h * g.tiles_n;
+  const int total = g.pair ? ((m_tiles_total + 1) / 2) * g.n_tiles * 2 : m_tiles_total * g.n_tiles;
+  const int grid = g.pair ? std::min(total, enc->num_sms & ~1) : std::min(total, enc->num_sms);
   std::pair<cudaEvent_t, cudaEvent_t>* ev = nullptr;
   if (enc->profile) {
     if (enc->prof_used == enc->prof_events.size()) {
@@ -593,11 +599,22 @@ int launch_conv(dad3d_encoder* enc, const Step& s, cudaStream_t stream) {
     cfg.blockDim = dim3(kGemmThreads);
     cfg.dynamicSmemBytes = gemm_smem_bytes(g);
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (enc->use_pdl) {
+      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
+    if (g.pair) {
+      attr[na].id = cudaLaunchAttributeClusterDimension;
+      attr[na].val.clusterDim.x = 2;
+      attr[na].val.clusterDim.y = 1;
+      attr[na].val.clusterDim.z = 1;
+      ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = enc->use_pdl ? 1 : 0;
+    cfg.numAttrs = na;
     if (enc->fp16) DAD3D_CUDA_OK(cudaLaunchKernelEx(&cfg, tile_gemm_kernel<EpiConvH>, s.maps, g, s.epi));
     else DAD3D_CUDA_OK(cudaLaunchKernelEx(&cfg, tile_gemm_kernel<EpiConv>, s.maps, g, s.epi));
   }
@@ -646,6 +663,8 @@ int dad3d_encoder_create(dad3d_encoder** out, const dad3d_conv_weights* layers, 
   {
     const char* e = std::getenv("DAD3D_PDL");
     enc->use_pdl = (e && e[0] == '1');
+    const char* e3 = std::getenv("DAD3D_PAIR");
+    enc->use_pair = (e3 && e3[0] == '1');
     const char* e2 = std::getenv("DAD3D_STEM_SIMT");
     enc->stem_simt = (e2 && e2[0] == '1');
   }

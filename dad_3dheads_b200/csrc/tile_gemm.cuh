@@ -74,6 +74,11 @@ struct GemmGeom {
                                    // cl_n*Ns+cj; the cl_n CTAs sharing a row tile each load 1/cl_n of the A tile and
                                    // TMA-multicast it to the others, likewise the cl_m CTAs sharing a column tile for B.
                                    // Operand traffic from L2 per CTA drops to A/cl_n + B/cl_m.
+  int pair;                        // 1: CTA pair (cluster of 2, tcgen05 cta_group::2): the pair computes a 256 x block_n tile,
+                                   // CTA r owns rows 128r.. (its own A tile and accumulator) and loads rows
+                                   // [r*block_n/2, (r+1)*block_n/2) of the B tile only; the leader (rank 0) issues every
+                                   // MMA (M = 256) and owns the full / tmem-empty barriers.  Operand bytes per CTA:
+                                   // A + B/2.  Requires cl_m == cl_n == 1, block_n == 128, sched 0.
   int sched;                       // 0: tiles round-robin over CTAs with the column tile fastest (default);
                                    // 1: row-tile persistent -- CTA b owns row tiles b, b+grid, ... and walks ALL column
                                    //    tiles of each (per-row-tile epilogue state is loaded once; all CTAs sweep the
@@ -88,7 +93,7 @@ struct GemmMaps {
 };
 
 __host__ __device__ inline int gemm_stage_bytes(const GemmGeom& g) {
-  return g.nA * kTileABytes + g.nB * g.block_n * kBlockK * 2;
+  return g.nA * kTileABytes + g.nB * (g.block_n >> g.pair) * kBlockK * 2;
 }
 __host__ inline int gemm_fixed_smem_bytes(int extra = 0) {
   return kEpiWarps * kStageOutBytes + extra + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -123,7 +128,14 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmGeom& g, int m_tile, 
 __device__ __forceinline__ bool tile_at(const GemmGeom& g, int i, TileCoord* tc) {
   const int m_tiles = g.tiles_w * g.tiles_h * g.tiles_n;
   int m, n;
-  if (g.sched == 0) {
+  if (g.pair) {
+    // pairs walk (row-tile pair, column tile) round-robin with the column tile fastest; a trailing odd row tile leaves the
+    // second CTA a ghost tile (zero-filled loads, clipped stores) so both CTAs run the same pipeline steps
+    const int t = static_cast<int>(blockIdx.x >> 1) + i * static_cast<int>(gridDim.x >> 1);
+    if (t >= ((m_tiles + 1) >> 1) * g.n_tiles) return false;
+    n = t % g.n_tiles;
+    m = (t / g.n_tiles) * 2 + static_cast<int>(ptx::cluster_ctarank());
+  } else if (g.sched == 0) {
     const int t = static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x);
     if (t >= m_tiles * g.n_tiles) return false;
     n = t % g.n_tiles;
@@ -161,6 +173,7 @@ struct EpiCtx {
   uint8_t* extra;    // Epi::kExtraSmemBytes of CTA-wide shared memory (epilogue-specific use)
   int prev_m_tile;   // row tile of the previous tile this CTA processed (-1 for the first)
   uint64_t* tempty;  // arrive here (every epilogue thread, once) when the accumulator has been drained into registers
+  uint32_t tempty_cluster;   // CTA-pair mode: shared::cluster address of the LEADER's tmem-empty barrier (0 = use tempty)
   // this thread's accumulator row
   int n, h, w;
   bool valid;
@@ -208,7 +221,8 @@ __device__ __forceinline__ void epi_load16(const EpiCtx& c, int c0, float (&x)[N
 }
 __device__ __forceinline__ void epi_release_tmem(const EpiCtx& c) {
   ptx::tc_fence_before();
-  ptx::mbar_arrive(c.tempty);
+  if (c.tempty_cluster) ptx::mbar_arrive_cluster(c.tempty_cluster);
+  else ptx::mbar_arrive(c.tempty);
 }
 // 32-column chunks [cb, ce) of the tile that column group grp handles
 __device__ __forceinline__ void epi_chunk_range(const GemmGeom& g, int grp, int* cb, int* ce) {
@@ -249,24 +263,29 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
     const int n_peers = g.cl_m + g.cl_n - 1;       // CTAs that read what I multicast == CTAs that multicast to me
     for (int s = 0; s < g.stages; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
-      ptx::mbar_init(&empty_bar[s], n_peers);     // a slot is free when every consumer of my slices has released it
+      ptx::mbar_init(&empty_bar[s], g.pair ? 1 : n_peers);   // a slot is free when every consumer of my slices has released it
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(&tfull_bar[b], 1);
-      ptx::mbar_init(&tempty_bar[b], kEpiWarps * 32);
+      ptx::mbar_init(&tempty_bar[b], (g.pair ? 2 : 1) * kEpiWarps * 32);   // pair: both CTAs' epilogues release the leader's
     }
     ptx::fence_mbar_init();
   }
   if (warp == 0) {
-    ptx::tmem_alloc(tmem_slot, kTmemCols);
-    ptx::tmem_relinquish();
+    if (g.pair) {
+      ptx::tmem_alloc_2sm(tmem_slot, kTmemCols);
+      ptx::tmem_relinquish_2sm();
+    } else {
+      ptx::tmem_alloc(tmem_slot, kTmemCols);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // ---- cluster bookkeeping (csize == 1: everything below degenerates to the single-CTA protocol)
-  const int csize = g.cl_m * g.cl_n;
+  const int csize = g.pair ? 2 : g.cl_m * g.cl_n;
   const int crank = csize > 1 ? static_cast<int>(ptx::cluster_ctarank()) : 0;
   const int ci = crank / g.cl_n, cj = crank % g.cl_n;
   uint16_t mask_a = 0, mask_b = 0;                 // CTAs sharing my row tile (A) / my column tile (B)
@@ -292,7 +311,28 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
             uint8_t* st = smem + stage * stage_bytes;
             const int r = kb - num_kb;
-            if (g.res_kind == 0) {
+            if (g.pair) {
+              // CTA pair: my A tile and my half of the B rows; every byte of both CTAs is accounted on the leader's barrier
+              const uint32_t lead_full = ptx::mapa_u32(&full_bar[stage], 0);
+              const int b_half = (g.block_n >> 1) * kBlockK * 2;
+              const int b_row = tc.n_tile * g.block_n + crank * (g.block_n >> 1);
+              uint8_t* sb2 = st + g.nA * kTileABytes;
+              if (g.res_kind == 0) {
+                if (crank == 0)
+                  ptx::mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(2 * (g.nA * kTileABytes + b_half)));
+                const int rc = tc.n_tile * g.block_n + r * kBlockK;
+                for (int i = 0; i < g.nA; ++i)
+                  ptx::tma_load_4d_2sm(st + i * kTileABytes, &maps.r[i], lead_full, rc, tc.w0, tc.h0, tc.n0);
+                ptx::tma_load_2d_2sm(sb2, &maps.b[0], lead_full, num_kb * kBlockK + rc, b_row);
+              } else {
+                if (crank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * tx_bytes);
+                for (int i = 0; i < g.nA; ++i)
+                  ptx::tma_load_4d_2sm(st + i * kTileABytes, &maps.r[i], lead_full, r * kBlockK, tc.w0 * g.res_stride,
+                                       tc.h0 * g.res_stride, tc.n0);
+                for (int i = 0; i < g.nB; ++i)
+                  ptx::tma_load_2d_2sm(sb2 + i * b_half, &maps.b[i], lead_full, (num_kb + r) * kBlockK, b_row);
+              }
+            } else if (g.res_kind == 0) {
               // identity residual: A = residual tile (the tile's own channels), B = identity columns (piece 0 only: the
               // other planes are zero there and are never multiplied)
               ptx::mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(g.nA * kTileABytes + g.block_n * kBlockK * 2));
@@ -320,13 +360,22 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
           const int r = tap / g.S;
           const int s = tap - r * g.S;
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
-          ptx::mbar_expect_tx(&full_bar[stage], tx_bytes);
+          if (!g.pair) ptx::mbar_expect_tx(&full_bar[stage], tx_bytes);
+          else if (crank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * tx_bytes);
           uint8_t* st = smem + stage * stage_bytes;
           const int cw = tc.w0 * g.stride + s - g.pad_w;
           const int ch = tc.h0 * g.stride + r - g.pad_h;
           uint8_t* sb = st + g.nA * kTileABytes;
           const int kcol = kb * kBlockK;
-          if (csize == 1) {
+          if (g.pair) {
+            const uint32_t lead_full = ptx::mapa_u32(&full_bar[stage], 0);
+            const int b_half = (g.block_n >> 1) * kBlockK * 2;
+            for (int i = 0; i < g.nA; ++i)
+              ptx::tma_load_4d_2sm(st + i * kTileABytes, &maps.a[i], lead_full, cb * kBlockK, cw, ch, tc.n0);
+            for (int i = 0; i < g.nB; ++i)
+              ptx::tma_load_2d_2sm(sb + i * b_half, &maps.b[i], lead_full, kcol,
+                                   tc.n_tile * g.block_n + crank * (g.block_n >> 1));
+          } else if (csize == 1) {
             for (int i = 0; i < g.nA; ++i)
               ptx::tma_load_4d(st + i * kTileABytes, &maps.a[i], &full_bar[stage], cb * kBlockK, cw, ch, tc.n0);
             for (int i = 0; i < g.nB; ++i)
@@ -348,8 +397,9 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer (single thread)
-    if (lane == 0) {
-      const uint32_t idesc = ptx::make_idesc_f16(g.fmt16, kBlockM, static_cast<uint32_t>(g.block_n));
+    if (lane == 0 && (!g.pair || crank == 0)) {
+      const uint32_t idesc = ptx::make_idesc_f16(g.fmt16, g.pair ? 2 * kBlockM : kBlockM, static_cast<uint32_t>(g.block_n));
+      const int b_piece_bytes = (g.block_n >> g.pair) * kBlockK * 2;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -371,21 +421,24 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
             const int pa = res_block ? g.mma_res_a[i] : g.mma_a[i];
             const int pb = res_block ? 0 : g.mma_b[i];
             const uint64_t adesc = ptx::make_kmajor_sw128_desc(sa + pa * kTileABytes);
-            const uint64_t bdesc = ptx::make_kmajor_sw128_desc(sb + pb * g.block_n * kBlockK * 2);
+            const uint64_t bdesc = ptx::make_kmajor_sw128_desc(sb + pb * b_piece_bytes);
             const uint32_t a_id = static_cast<uint32_t>(res_block ? g.mma_res_acc[i] : g.mma_acc[i]);
             const uint32_t d_acc = d_tmem + a_id * static_cast<uint32_t>(g.block_n);
 #pragma unroll
             for (int k = 0; k < kBlockK / 16; ++k) {
               // advancing 16 elements (32 B) along K inside the 128 B swizzle row = +2 in the (addr >> 4) field
-              ptx::umma_f16(d_acc, adesc + 2u * k, bdesc + 2u * k, idesc, (started >> a_id) & 1u);
+              if (g.pair) ptx::umma_f16_2sm(d_acc, adesc + 2u * k, bdesc + 2u * k, idesc, (started >> a_id) & 1u);
+              else ptx::umma_f16(d_acc, adesc + 2u * k, bdesc + 2u * k, idesc, (started >> a_id) & 1u);
               started |= 1u << a_id;
             }
           }
-          if (csize == 1) ptx::umma_commit(&empty_bar[stage]);   // smem slot reusable once these MMAs have read it
+          if (g.pair) ptx::umma_commit_2sm_mc(&empty_bar[stage], 3);   // both CTAs' slots were read by these MMAs
+          else if (csize == 1) ptx::umma_commit(&empty_bar[stage]);   // smem slot reusable once these MMAs have read it
           else ptx::umma_commit_mc(&empty_bar[stage], mask_peers);   // ... tell every CTA that fills this slot
           if (++stage == g.stages) { stage = 0; phase ^= 1u; }
         }
-        ptx::umma_commit(&tfull_bar[acc]);        // accumulator complete
+        if (g.pair) ptx::umma_commit_2sm_mc(&tfull_bar[acc], 3);   // both halves of the accumulator are complete
+        else ptx::umma_commit(&tfull_bar[acc]);   // accumulator complete
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -421,6 +474,7 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
       c.bh0 = c.tc.h0 + bih;
       c.bn0 = c.tc.n0 + bin;
       c.tempty = &tempty_bar[acc];
+      c.tempty_cluster = g.pair ? ptx::mapa_u32(&tempty_bar[acc], 0) : 0u;
       c.t_acc = tmem_base + (static_cast<uint32_t>(c.wq * 32) << 16) + static_cast<uint32_t>(acc * g.n_acc * g.block_n);
       Epi::prefetch(ep, c, user_state);            // global reads that do not depend on the accumulator overlap the main loop
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
@@ -438,7 +492,8 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
   if (csize > 1) ptx::cluster_sync_all();          // nobody leaves while a peer may still write my smem / barriers
   if (warp == 0) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, kTmemCols);
+    if (g.pair) ptx::tmem_dealloc_2sm(tmem_base, kTmemCols);
+    else ptx::tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 

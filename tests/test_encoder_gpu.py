@@ -1,7 +1,8 @@
 """-m gpu: the CUDA encoder (through the C ABI) against the CPU oracle's FlameRegression.forward, same seeded weights/inputs.
 
 Tolerances (norm-wise relative L2 vs the fp64 oracle; north_star contract: 1e-4 relative to the fp32 reference path):
-  "fp32"   (bf16 three-way split, 6 products, two-class accumulation)   < 3e-5   -- the parity mode
+  "fp32"   (bf16 three-way split, 6 products, two-class accumulation)   < 3e-5   -- strict-operand parity mode
+  "fp16x2" (fp16 hi/lo, 3 products, per-channel scaled weights)          < 5e-5   -- bench default, also under the 1e-4 contract
   "bf16x2" (bf16 hi/lo, 3 products)                                      < 1e-4
   "bf16"   (plain bf16 operands, throughput mode, BASELINE config 3)     < 2e-2   (NOT under the 1e-4 banner)
 """
@@ -33,7 +34,7 @@ def ref5(sd):
     return x, out
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32", 3e-5), ("bf16x2", 1e-4), ("bf16", 2e-2)])
+@pytest.mark.parametrize("precision,tol", [("fp32", 3e-5), ("fp16x2", 5e-5), ("bf16x2", 1e-4), ("fp16", 5e-3), ("bf16", 2e-2)])
 def test_encoder_matches_oracle(sd, ref5, cuda_device, precision, tol):
     from dad_3dheads_b200.encoder import Dad3dEncoder
     x, ref = ref5
@@ -45,13 +46,14 @@ def test_encoder_matches_oracle(sd, ref5, cuda_device, precision, tol):
     assert all(e < tol for e in errs.values()), errs
 
 
-def test_fp32_mode_elementwise_contract(sd, ref5, cuda_device):
+@pytest.mark.parametrize("precision", ["fp32", "fp16x2"])
+def test_elementwise_contract(sd, ref5, cuda_device, precision):
     """|err| <= 1e-4 * |ref| + 1e-4 on every one of the 413 params (values span +-3), vs the fp32 oracle itself."""
     from dad_3dheads_b200.encoder import Dad3dEncoder
     x, _ = ref5
     with torch.no_grad():
         ref32 = flame_regression_forward(x, sd)
-    out = Dad3dEncoder(sd, cuda_device, precision="fp32")(x.to(cuda_device))
+    out = Dad3dEncoder(sd, cuda_device, precision=precision)(x.to(cuda_device))
     p, r = out[OUTPUT_3DMM_PARAMS].cpu(), ref32[OUTPUT_3DMM_PARAMS]
     assert ((p - r).abs() <= 1e-4 * r.abs() + 1e-4).all(), (p - r).abs().max()
 
@@ -109,6 +111,19 @@ def test_batch_64_matches_oracle_subset(sd, cuda_device):
         ref = flame_regression_forward(x[sel].double(), {k: v.double() for k, v in sd.items()})
     assert _rel(p[sel], ref[OUTPUT_3DMM_PARAMS]) < 3e-5 and _rel(l[sel], ref[OUTPUT_2D_LANDMARKS]) < 3e-5
     assert torch.isfinite(p).all()
+
+
+def test_cta_pair_mode_is_bit_identical(sd, cuda_device, monkeypatch):
+    """DAD3D_PAIR=1 runs the large layers on cta_group::2 CTA pairs (256-row tiles, B split across the pair): the same
+    products in the same order, so the outputs must equal the single-CTA path bit for bit (batch 64: pairs only engage
+    when every SM pair has work)."""
+    from dad_3dheads_b200.encoder import Dad3dEncoder
+    x = torch.randn(64, 3, 256, 256, generator=torch.Generator().manual_seed(65)).to(cuda_device)
+    base = Dad3dEncoder(sd, cuda_device, precision="fp16x2", want_heatmap=False).forward_raw(x)
+    monkeypatch.setenv("DAD3D_PAIR", "1")
+    pair = Dad3dEncoder(sd, cuda_device, precision="fp16x2", want_heatmap=False).forward_raw(x)
+    monkeypatch.delenv("DAD3D_PAIR")
+    assert torch.equal(base[0], pair[0]) and torch.equal(base[1], pair[1])
 
 
 def test_encoder_golden_fixture(sd, cuda_device):
