@@ -573,6 +573,8 @@ int launch_conv(dad3d_encoder* enc, const Step& s, cudaStream_t stream) {
   if (!configured) {
     DAD3D_CUDA_OK(cudaFuncSetAttribute(tile_gemm_kernel<EpiConv>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemLimit));
     DAD3D_CUDA_OK(cudaFuncSetAttribute(tile_gemm_kernel<EpiConvH>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemLimit));
+    DAD3D_CUDA_OK(cudaFuncSetAttribute(tile_gemm_kernel<EpiConvH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemLimit));
+    DAD3D_CUDA_OK(cudaFuncSetAttribute(tile_gemm_kernel<EpiConv, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemLimit));
     configured = true;
   }
   const GemmGeom& g = s.geom;
@@ -615,8 +617,13 @@ int launch_conv(dad3d_encoder* enc, const Step& s, cudaStream_t stream) {
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    if (enc->fp16) DAD3D_CUDA_OK(cudaLaunchKernelEx(&cfg, tile_gemm_kernel<EpiConvH>, s.maps, g, s.epi));
-    else DAD3D_CUDA_OK(cudaLaunchKernelEx(&cfg, tile_gemm_kernel<EpiConv>, s.maps, g, s.epi));
+    if (g.pair) {
+      if (enc->fp16) DAD3D_CUDA_OK(cudaLaunchKernelEx(&cfg, tile_gemm_kernel<EpiConvH, true>, s.maps, g, s.epi));
+      else DAD3D_CUDA_OK(cudaLaunchKernelEx(&cfg, tile_gemm_kernel<EpiConv, true>, s.maps, g, s.epi));
+    } else {
+      if (enc->fp16) DAD3D_CUDA_OK(cudaLaunchKernelEx(&cfg, tile_gemm_kernel<EpiConvH>, s.maps, g, s.epi));
+      else DAD3D_CUDA_OK(cudaLaunchKernelEx(&cfg, tile_gemm_kernel<EpiConv>, s.maps, g, s.epi));
+    }
   }
   count_launch();
   if (ev) DAD3D_CUDA_OK(cudaEventRecord(ev->second, stream));

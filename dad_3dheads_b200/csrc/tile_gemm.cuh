@@ -232,7 +232,9 @@ __device__ __forceinline__ void epi_chunk_range(const GemmGeom& g, int grp, int*
   *ce = min(nch, *cb + per);
 }
 
-template <class Epi>
+// kPair = true is the cta_group::2 build (must be launched as clusters of 2 with g.pair == 1); the default build contains no
+// CTA-pair instruction, so it launches without a cluster attribute.
+template <class Epi, bool kPair = false>
 // 10 warps = up to 3 warps on one SM sub-partition (16 K registers each) -> at most 168 registers per thread
 __global__ void __launch_bounds__(kGemmThreads, 1)
 tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const typename Epi::Params ep) {
@@ -263,16 +265,16 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
     const int n_peers = g.cl_m + g.cl_n - 1;       // CTAs that read what I multicast == CTAs that multicast to me
     for (int s = 0; s < g.stages; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
-      ptx::mbar_init(&empty_bar[s], g.pair ? 1 : n_peers);   // a slot is free when every consumer of my slices has released it
+      ptx::mbar_init(&empty_bar[s], kPair ? 1 : n_peers);   // a slot is free when every consumer of my slices has released it
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(&tfull_bar[b], 1);
-      ptx::mbar_init(&tempty_bar[b], (g.pair ? 2 : 1) * kEpiWarps * 32);   // pair: both CTAs' epilogues release the leader's
+      ptx::mbar_init(&tempty_bar[b], (kPair ? 2 : 1) * kEpiWarps * 32);   // pair: both CTAs' epilogues release the leader's
     }
     ptx::fence_mbar_init();
   }
   if (warp == 0) {
-    if (g.pair) {
+    if constexpr (kPair) {
       ptx::tmem_alloc_2sm(tmem_slot, kTmemCols);
       ptx::tmem_relinquish_2sm();
     } else {
@@ -285,7 +287,7 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // ---- cluster bookkeeping (csize == 1: everything below degenerates to the single-CTA protocol)
-  const int csize = g.pair ? 2 : g.cl_m * g.cl_n;
+  const int csize = kPair ? 2 : g.cl_m * g.cl_n;
   const int crank = csize > 1 ? static_cast<int>(ptx::cluster_ctarank()) : 0;
   const int ci = crank / g.cl_n, cj = crank % g.cl_n;
   uint16_t mask_a = 0, mask_b = 0;                 // CTAs sharing my row tile (A) / my column tile (B)
@@ -311,7 +313,7 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
             uint8_t* st = smem + stage * stage_bytes;
             const int r = kb - num_kb;
-            if (g.pair) {
+            if constexpr (kPair) {
               // CTA pair: my A tile and my half of the B rows; every byte of both CTAs is accounted on the leader's barrier
               const uint32_t lead_full = ptx::mapa_u32(&full_bar[stage], 0);
               const int b_half = (g.block_n >> 1) * kBlockK * 2;
@@ -360,14 +362,14 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
           const int r = tap / g.S;
           const int s = tap - r * g.S;
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
-          if (!g.pair) ptx::mbar_expect_tx(&full_bar[stage], tx_bytes);
+          if (!kPair) ptx::mbar_expect_tx(&full_bar[stage], tx_bytes);
           else if (crank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * tx_bytes);
           uint8_t* st = smem + stage * stage_bytes;
           const int cw = tc.w0 * g.stride + s - g.pad_w;
           const int ch = tc.h0 * g.stride + r - g.pad_h;
           uint8_t* sb = st + g.nA * kTileABytes;
           const int kcol = kb * kBlockK;
-          if (g.pair) {
+          if constexpr (kPair) {
             const uint32_t lead_full = ptx::mapa_u32(&full_bar[stage], 0);
             const int b_half = (g.block_n >> 1) * kBlockK * 2;
             for (int i = 0; i < g.nA; ++i)
@@ -397,9 +399,9 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer (single thread)
-    if (lane == 0 && (!g.pair || crank == 0)) {
-      const uint32_t idesc = ptx::make_idesc_f16(g.fmt16, g.pair ? 2 * kBlockM : kBlockM, static_cast<uint32_t>(g.block_n));
-      const int b_piece_bytes = (g.block_n >> g.pair) * kBlockK * 2;
+    if (lane == 0 && (!kPair || crank == 0)) {
+      const uint32_t idesc = ptx::make_idesc_f16(g.fmt16, kPair ? 2 * kBlockM : kBlockM, static_cast<uint32_t>(g.block_n));
+      const int b_piece_bytes = (g.block_n >> (kPair ? 1 : 0)) * kBlockK * 2;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -427,17 +429,17 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
 #pragma unroll
             for (int k = 0; k < kBlockK / 16; ++k) {
               // advancing 16 elements (32 B) along K inside the 128 B swizzle row = +2 in the (addr >> 4) field
-              if (g.pair) ptx::umma_f16_2sm(d_acc, adesc + 2u * k, bdesc + 2u * k, idesc, (started >> a_id) & 1u);
+              if constexpr (kPair) ptx::umma_f16_2sm(d_acc, adesc + 2u * k, bdesc + 2u * k, idesc, (started >> a_id) & 1u);
               else ptx::umma_f16(d_acc, adesc + 2u * k, bdesc + 2u * k, idesc, (started >> a_id) & 1u);
               started |= 1u << a_id;
             }
           }
-          if (g.pair) ptx::umma_commit_2sm_mc(&empty_bar[stage], 3);   // both CTAs' slots were read by these MMAs
+          if constexpr (kPair) ptx::umma_commit_2sm_mc(&empty_bar[stage], 3);   // both CTAs' slots were read by these MMAs
           else if (csize == 1) ptx::umma_commit(&empty_bar[stage]);   // smem slot reusable once these MMAs have read it
           else ptx::umma_commit_mc(&empty_bar[stage], mask_peers);   // ... tell every CTA that fills this slot
           if (++stage == g.stages) { stage = 0; phase ^= 1u; }
         }
-        if (g.pair) ptx::umma_commit_2sm_mc(&tfull_bar[acc], 3);   // both halves of the accumulator are complete
+        if constexpr (kPair) ptx::umma_commit_2sm_mc(&tfull_bar[acc], 3);   // both halves of the accumulator are complete
         else ptx::umma_commit(&tfull_bar[acc]);   // accumulator complete
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
@@ -474,7 +476,7 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
       c.bh0 = c.tc.h0 + bih;
       c.bn0 = c.tc.n0 + bin;
       c.tempty = &tempty_bar[acc];
-      c.tempty_cluster = g.pair ? ptx::mapa_u32(&tempty_bar[acc], 0) : 0u;
+      c.tempty_cluster = kPair ? ptx::mapa_u32(&tempty_bar[acc], 0) : 0u;
       c.t_acc = tmem_base + (static_cast<uint32_t>(c.wq * 32) << 16) + static_cast<uint32_t>(acc * g.n_acc * g.block_n);
       Epi::prefetch(ep, c, user_state);            // global reads that do not depend on the accumulator overlap the main loop
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
@@ -492,7 +494,7 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
   if (csize > 1) ptx::cluster_sync_all();          // nobody leaves while a peer may still write my smem / barriers
   if (warp == 0) {
     ptx::tc_fence_after();
-    if (g.pair) ptx::tmem_dealloc_2sm(tmem_base, kTmemCols);
+    if constexpr (kPair) ptx::tmem_dealloc_2sm(tmem_base, kTmemCols);
     else ptx::tmem_dealloc(tmem_base, kTmemCols);
   }
 }

@@ -26,8 +26,8 @@ def load(fn):
 
 
 def one_step(rows):
-    """Launches from one stem_conv_kernel to the next (the steps are identical)."""
-    idx = [i for i, r in enumerate(rows) if "stem_conv" in r["name"]]
+    """Launches from one stem kernel (s2d or SIMT conv) to the next (the steps are identical)."""
+    idx = [i for i, r in enumerate(rows) if "stem_conv" in r["name"] or "stem_s2d" in r["name"]]
     if len(idx) >= 2:
         return rows[idx[0]:idx[1]]
     if idx:                                   # window started mid-step: the part before it belongs to the same (identical) step
