@@ -53,6 +53,8 @@ SIGNATURES = {
                                          C.c_void_p, C.c_size_t, C.c_void_p]),
     "dad3d_preprocess": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dad3d_preprocess_batch": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dad3d_encoder_set_profile": (C.c_int, [C.c_void_p, C.c_int32]),
     "dad3d_encoder_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong),
                                               C.POINTER(C.c_double)]),

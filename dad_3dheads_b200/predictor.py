@@ -103,6 +103,8 @@ class FaceMeshPredictor:
         self._img_size = config["img_size"]
         self._stride = config.get("stride", 2)
         self._static = None
+        self._lm_index: Dict[str, Tensor] = {}
+        self._graphs: Dict[Any, Any] = {}
 
     # ------------------------------------------------------------------ reference single-image API
     def __call__(self, x: Any) -> Any:
@@ -205,13 +207,25 @@ class FaceMeshPredictor:
         """images: list of HxWx3 uint8 RGB arrays/tensors (any sizes).  -> [B,3,S,S] fp32 on the GPU, bit-identical to
         ``_transform`` (cv2 INTER_LINEAR letter-box + constant-0 pad + imagenet normalisation); only the raw uint8
         pixels cross the PCIe bus."""
-        import ctypes as C
         lib = _lib.load()
         S = self._img_size
-        out = torch.empty(len(images), 3, S, S, dtype=torch.float32, device=self.device)
         mean = (np.array(_MEAN, dtype=np.float32) * 255.0).astype(np.float32)
         inv = np.reciprocal(np.array(_STD, dtype=np.float32) * 255.0, dtype=np.float32)
         stream = torch.cuda.current_stream(self.device).cuda_stream
+        if isinstance(images, Tensor) and images.ndim == 4:
+            # one [B,H,W,3] uint8 tensor (host, ideally pinned, or device): one copy, one launch
+            assert images.dtype == torch.uint8 and images.shape[3] == 3
+            B, h, w = int(images.shape[0]), int(images.shape[1]), int(images.shape[2])
+            scale = S / float(max(h, w))
+            nh, nw = (py3round(h * scale), py3round(w * scale)) if scale != 1.0 else (h, w)
+            out = torch.empty(B, 3, S, S, dtype=torch.float32, device=self.device)
+            with torch.cuda.device(self.device):
+                d = images.contiguous().to(self.device, non_blocking=True)
+                _lib.check(lib.dad3d_preprocess_batch(d.data_ptr(), B, h, w, nh, nw, S, mean.ctypes.data, inv.ctypes.data,
+                                                      out.data_ptr(), stream), "dad3d_preprocess_batch")
+                d.record_stream(torch.cuda.current_stream(self.device))
+            return out
+        out = torch.empty(len(images), 3, S, S, dtype=torch.float32, device=self.device)
         keep = []
         with torch.cuda.device(self.device):
             for i, im in enumerate(images):
@@ -228,17 +242,25 @@ class FaceMeshPredictor:
 
     # ------------------------------------------------------------------ batched device-resident API (new)
     def _landmark_index(self, subset: str) -> Tensor:
-        if self._static is None:
-            self._static = load_flame_static()
-        key = {"191": "keypoints_191", "445": "keypoints_445", "565": "keypoints_565"}[str(subset)]
-        return torch.from_numpy(self._static[key].astype(np.int64)).to(self.device)
+        subset = str(subset)
+        if subset not in self._lm_index:                     # uploaded once (no per-call H2D copy; graph-capture safe)
+            if self._static is None:
+                self._static = load_flame_static()
+            key = {"191": "keypoints_191", "445": "keypoints_445", "565": "keypoints_565"}[subset]
+            self._lm_index[subset] = torch.from_numpy(self._static[key].astype(np.int64)).to(self.device)
+        return self._lm_index[subset]
 
     def predict_batch(self, images: Tensor, landmark_subset: Optional[str] = "445", to_2d: bool = True,
                       fast_decode: bool = False) -> Dict[str, Tensor]:
-        """images: [B,3,256,256] fp32 already letter-boxed + normalised (host or device).  All outputs stay on the GPU:
-        "3dmm_params" [B,413], "points" [B,68,2] (pixels of the 256x256 input), "3d_vertices" [B,5023,3],
+        """images: [B,3,256,256] fp32 already letter-boxed + normalised, or raw RGB as the reference's ``__call__`` takes it:
+        one [B,H,W,3] uint8 tensor / a list of HxWx3 uint8 images (letter-boxed + normalised on the GPU, bit-identical to
+        the reference's albumentations pipeline); host or device.  All outputs stay on the GPU:
+        "3dmm_params" [B,413], "points" [B,68,2] (pixels of the 256x256 network input), "3d_vertices" [B,5023,3],
         "projected_vertices" [B,5023,2|3], "landmarks_<subset>" [B,L,2|3]."""
-        x = images.to(self.device, torch.float32, non_blocking=True)
+        if isinstance(images, (list, tuple)) or (isinstance(images, Tensor) and images.dtype == torch.uint8):
+            x = self.preprocess_batch(images)
+        else:
+            x = images.to(self.device, torch.float32, non_blocking=True)
         params, lms, _ = self.model.forward_raw(x, want_heatmap=False)
         v3, proj = self.head_mesh.decode(params, to_2d=to_2d, fast=fast_decode)
         out = {"3dmm_params": params, "points": lms * float(self._img_size), "3d_vertices": v3,
@@ -246,4 +268,33 @@ class FaceMeshPredictor:
         if landmark_subset is not None:
             dec = self.head_mesh.flame.decoder(self.device)
             out[f"landmarks_{landmark_subset}"] = dec.gather(proj, self._landmark_index(landmark_subset))
+        return out
+
+    def predict_batch_graphed(self, images: Tensor, landmark_subset: Optional[str] = "445", to_2d: bool = True,
+                              fast_decode: bool = False) -> Dict[str, Tensor]:
+        """:meth:`predict_batch` replayed from a CUDA graph (one graph per input shape / dtype / option set): the ~110 kernel
+        launches of a step become one graph launch, which removes the launch gaps between the many sub-20 us layers.
+        ``images`` is copied into the graph's static input buffer (host or device source); the returned tensors are the
+        graph's static outputs -- consume or clone them before the next call with the same signature."""
+        assert isinstance(images, Tensor), "the graphed path takes one tensor ([B,3,S,S] fp32 or [B,H,W,3] uint8)"
+        key = (tuple(images.shape), images.dtype, landmark_subset, to_2d, fast_decode)
+        ent = self._graphs.get(key)
+        if ent is None:
+            static_in = torch.empty(images.shape, dtype=images.dtype, device=self.device)
+            static_in.copy_(images, non_blocking=True)
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):                     # warm-up: plans, workspaces, tensor maps, index tables
+                for _ in range(2):
+                    self.predict_batch(static_in, landmark_subset, to_2d, fast_decode)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self.predict_batch(static_in, landmark_subset, to_2d, fast_decode)
+            ent = (graph, static_in, out)
+            self._graphs[key] = ent
+        graph, static_in, out = ent
+        static_in.copy_(images, non_blocking=True)
+        graph.replay()
         return out

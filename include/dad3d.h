@@ -147,6 +147,10 @@ DAD3D_API int dad3d_encoder_forward(dad3d_encoder* enc, const float* images_d, i
 DAD3D_API int dad3d_preprocess(const uint8_t* image_d, int32_t H, int32_t W, int32_t new_h, int32_t new_w,
                                int32_t img_size, const float* mean255_h, const float* inv_std255_h, float* out_d,
                                dad3d_stream stream);
+/* the same for B images of one size: images_d [B,H,W,3] uint8 -> out_d [B,3,img_size,img_size] fp32, one launch */
+DAD3D_API int dad3d_preprocess_batch(const uint8_t* images_d, int32_t B, int32_t H, int32_t W, int32_t new_h, int32_t new_w,
+                                     int32_t img_size, const float* mean255_h, const float* inv_std255_h, float* out_d,
+                                     dad3d_stream stream);
 
 /* Live timing of the dominant kernel (the tcgen05 tile engine) for bench.py's roofline: while on, every conv / linear
  * launch is bracketed by CUDA events on the launching stream.  profile_read synchronises those events and returns their

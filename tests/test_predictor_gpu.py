@@ -69,3 +69,18 @@ def test_vertex_l2_error_target(predictor, oracle):
     want = oracle.predict_batch(x)
     l2 = (got["3d_vertices"].double().cpu() - want["3d_vertices"]).norm(dim=-1)
     assert l2.max().item() < 1e-4, l2.max().item()
+
+
+def test_graph_replay_equals_eager(predictor, cuda_device):
+    """predict_batch_graphed replays predict_batch from a CUDA graph: bit-identical outputs, for fp32 and raw uint8
+    input, and across consecutive calls with different data (static input buffer refreshed every call)."""
+    g = torch.Generator().manual_seed(5)
+    for make in (lambda: torch.randn(3, 3, 256, 256, generator=g),
+                 lambda: torch.randint(0, 256, (3, 256, 256, 3), generator=g, dtype=torch.uint8)):
+        for _ in range(2):
+            x = make()
+            want = {k: v.clone() for k, v in predictor.predict_batch(x).items()}
+            got = predictor.predict_batch_graphed(x)
+            torch.cuda.synchronize()
+            for k in want:
+                assert torch.equal(got[k], want[k]), k

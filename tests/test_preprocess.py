@@ -45,3 +45,21 @@ def test_device_preprocess_bit_exact(cuda_device):
     for i, im in enumerate(imgs):
         want = np.transpose(letterbox_normalise(im, 256), (2, 0, 1))
         assert np.array_equal(got[i], want), sizes[i]
+
+
+@pytest.mark.gpu
+def test_device_preprocess_same_size_batch(cuda_device):
+    """[B,H,W,3] uint8 tensor -> one dad3d_preprocess_batch launch; predict_batch accepts the raw batch directly."""
+    import torch
+    from dad_3dheads_b200.encoder_weights import synthetic_state_dict
+    from dad_3dheads_b200.predictor import FaceMeshPredictor, letterbox_normalise
+    pred = FaceMeshPredictor.dad_3dnet(state_dict=synthetic_state_dict(0), precision="fp16x2")
+    for h, w in [(256, 256), (300, 411), (97, 64)]:
+        imgs = np.stack([_img(h, w, 50 + i) for i in range(3)])
+        got = pred.preprocess_batch(torch.from_numpy(imgs).pin_memory()).cpu().numpy()
+        for i in range(3):
+            assert np.array_equal(got[i], np.transpose(letterbox_normalise(imgs[i], 256), (2, 0, 1))), (h, w, i)
+    raw = torch.from_numpy(np.stack([_img(256, 256, 80 + i) for i in range(2)]))
+    a = pred.predict_batch(raw)
+    b = pred.predict_batch(pred.preprocess_batch(raw))
+    assert torch.equal(a["3dmm_params"], b["3dmm_params"]) and torch.equal(a["3d_vertices"], b["3d_vertices"])
