@@ -122,6 +122,7 @@ struct dad3d_encoder {
   std::unique_ptr<Plan> plan;
   size_t ws_cache_B = 0, ws_cache_bytes = 0;
   bool stem_simt = false;          // env DAD3D_STEM_SIMT=1: run the stem on the fp32 CUDA-core kernel instead of the tile engine
+  bool use_halo = false;           // env DAD3D_HALO=1: halo-reuse tiles for the 3x3 stride-1 layers
   bool use_pair = false;           // env DAD3D_PAIR=1: cta_group::2 CTA pairs for the large 128-wide layers
   bool use_pdl = false;            // programmatic dependent launch for the tile-engine kernels (env DAD3D_PDL=1 enables;
                                    // measured neutral on B200 at batch 64: 6689 vs 6764 heads/s, so off by default)
@@ -430,6 +431,11 @@ int make_plan(dad3d_encoder* enc, int B, void* ws, size_t ws_bytes, bool layout_
     GemmGeom& g = s.geom;
     std::memset(&g, 0, sizeof(g));
     pick_tile(Wo, Ho, &g.tw, &g.th, &g.tn);
+    // 3x3 / stride 1 / pad 1 layers: 8 x 16-pixel tiles whose nine taps share one halo patch in shared memory (tile_gemm.cuh
+    // "halo mode"); needs a map of at least 8 x 16 pixels and room for a two-deep weights ring (checked below)
+    bool halo = enc->use_halo && !s.stem && w->R == 3 && w->S == 3 && s.stride == 1 && s.pad == 1 && Wo >= kHaloTW &&
+                Ho >= kHaloTH;
+    if (halo) { g.tw = kHaloTW; g.th = kHaloTH; g.tn = 1; }
     g.tiles_w = ceil_div(Wo, g.tw);
     g.tiles_h = ceil_div(Ho, g.th);
     g.tiles_n = ceil_div(ti.N, g.tn);
@@ -467,8 +473,14 @@ int make_plan(dad3d_encoder* enc, int B, void* ws, size_t ws_bytes, bool layout_
     // CTA pairs (cta_group::2): each CTA of a pair loads only half of the B tile; worth it when every SM pair has work
     const bool pair = enc->use_pair && block_n == 128 && w->has_b64 &&
                       ((m_tiles + 1) / 2) * g.n_tiles >= enc->num_sms / 2;
-    g.pair = pair ? 1 : 0;
+    g.pair = (pair && !halo) ? 1 : 0;
     g.stages = gemm_max_stages(g);
+    if (halo) {
+      g.halo = 1;
+      g.stages = 2;
+      g.stages_b = gemm_halo_b_stages(g);
+      if (g.stages_b < 2) { set_error("layer " + w->name + ": halo pipeline does not fit shared memory"); return DAD3D_ERR_INVALID; }
+    }
     if (g.stages < 2) { set_error("layer " + w->name + ": pipeline does not fit shared memory"); return DAD3D_ERR_INVALID; }
     for (int p = 0; p < enc->P; ++p) {
       // stem: row x of the A operand is the 64-element window that starts at padded s2d pixel x (dim 1 advances by one
@@ -477,8 +489,8 @@ int make_plan(dad3d_encoder* enc, int B, void* ws, size_t ws_bytes, bool layout_
                                 static_cast<uint64_t>(ti.H), static_cast<uint64_t>(ti.N)};
       const uint64_t strides[3] = {static_cast<uint64_t>(ti.C) * 2, static_cast<uint64_t>(ti.W) * ti.C * 2,
                                    static_cast<uint64_t>(ti.H) * ti.W * ti.C * 2};
-      const uint32_t box[4] = {kBlockK, static_cast<uint32_t>(g.tw * s.stride), static_cast<uint32_t>(g.th * s.stride),
-                               static_cast<uint32_t>(g.tn)};
+      const uint32_t box[4] = {kBlockK, static_cast<uint32_t>(halo ? kHaloPW : g.tw * s.stride),
+                               static_cast<uint32_t>(halo ? kHaloPH : g.th * s.stride), static_cast<uint32_t>(g.tn)};
       const uint32_t es[4] = {1, static_cast<uint32_t>(s.stride), static_cast<uint32_t>(s.stride), 1};
       const uint16_t* basep = reinterpret_cast<const uint16_t*>(ti.ptr) + static_cast<size_t>(p) * ti.plane_elems();
       if (!make_tmap_16bit(&s.maps.a[p], basep, 4, dims, strides, box, es)) return DAD3D_ERR_CUDA;
@@ -670,6 +682,8 @@ int dad3d_encoder_create(dad3d_encoder** out, const dad3d_conv_weights* layers, 
   {
     const char* e = std::getenv("DAD3D_PDL");
     enc->use_pdl = (e && e[0] == '1');
+    const char* e4 = std::getenv("DAD3D_HALO");
+    enc->use_halo = (e4 && e4[0] == '1');
     const char* e3 = std::getenv("DAD3D_PAIR");
     enc->use_pair = (e3 && e3[0] == '1');
     const char* e2 = std::getenv("DAD3D_STEM_SIMT");

@@ -299,6 +299,20 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
+// Same with an explicit stride between 8-row groups (any multiple of 16 B) and a start address that is only 128-byte
+// aligned: the hardware applies the 128B swizzle to the final shared-memory address bits, so a view that starts at row j of
+// a TMA-written tile and steps 8-row groups by P rows reads exactly rows j + P*g + i (measured: tools/probes/
+// umma_halo_probe.cu, base offset field = 0 for every start).  This is what lets the nine taps of a 3x3 convolution share
+// one halo tile.
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
 // Instruction descriptor for kind::f16: fp32 accumulate, A and B both K-major, same 16-bit format.
 //   fmt16: 0 = fp16, 1 = bf16.   m in {64,128}, n % 16 == 0 (for m = 128), 16 <= n <= 256.
 __host__ __device__ __forceinline__ uint32_t make_idesc_f16(uint32_t fmt16, uint32_t m, uint32_t n) {

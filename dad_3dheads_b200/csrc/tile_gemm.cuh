@@ -39,6 +39,11 @@ constexpr int kGemmThreads = (kFirstEpiWarp + kEpiWarps) * 32;   // 320 threads
 constexpr int kTmemCols = 512;
 constexpr int kStageOutBytes = 4096;              // per epilogue warp: 32 rows x 128 B
 constexpr int kGemmSmemLimit = 227 * 1024;
+// halo mode (3x3 stride-1 convolutions): output tiles of 8 x 16 pixels, input halo patch of 10 x 18 pixels per 64-channel
+// block and piece = 180 rows of 128 B, padded to a multiple of 1024 B per piece
+constexpr int kHaloTW = 8, kHaloTH = 16, kHaloPW = kHaloTW + 2, kHaloPH = kHaloTH + 2;
+constexpr int kHaloBytes = kHaloPW * kHaloPH * kBlockK * 2;        // 23040
+constexpr int kHaloPieceBytes = 23 * 1024;                         // 23552
 
 struct GemmGeom {
   // output tile = tn images x th rows x tw columns of output pixels (tw*th*tn == 128); plain GEMM: tw=128, th=tn=1
@@ -74,6 +79,13 @@ struct GemmGeom {
                                    // cl_n*Ns+cj; the cl_n CTAs sharing a row tile each load 1/cl_n of the A tile and
                                    // TMA-multicast it to the others, likewise the cl_m CTAs sharing a column tile for B.
                                    // Operand traffic from L2 per CTA drops to A/cl_n + B/cl_m.
+  int halo;                        // 1: 3x3 / stride 1 / pad 1 convolution with HALO REUSE: tiles are 8 x 16 pixels of one image; per
+                                   // 64-channel block ONE (10 x 18)-pixel halo patch is loaded (A ring, `stages` deep) and all
+                                   // nine taps read it through descriptors that differ only in their start row (r*10 + s)
+                                   // with an 8-row-group stride of 10 rows; the weights stream tap by tap through their own
+                                   // ring (`stages_b` deep).  k order: channel block outer, tap inner.  A bytes per tile
+                                   // drop 9 x 16 KiB -> 22.5 KiB per block and piece.
+  int stages_b;                    // halo mode: depth of the B (weights) ring
   int pair;                        // 1: CTA pair (cluster of 2, tcgen05 cta_group::2): the pair computes a 256 x block_n tile,
                                    // CTA r owns rows 128r.. (its own A tile and accumulator) and loads rows
                                    // [r*block_n/2, (r+1)*block_n/2) of the B tile only; the leader (rank 0) issues every
@@ -95,14 +107,22 @@ struct GemmMaps {
 __host__ __device__ inline int gemm_stage_bytes(const GemmGeom& g) {
   return g.nA * kTileABytes + g.nB * (g.block_n >> g.pair) * kBlockK * 2;
 }
+__host__ __device__ inline int gemm_halo_a_stage_bytes(const GemmGeom& g) { return g.nA * kHaloPieceBytes; }
+__host__ __device__ inline int gemm_b_stage_bytes(const GemmGeom& g) { return g.nB * g.block_n * kBlockK * 2; }
 __host__ inline int gemm_fixed_smem_bytes(int extra = 0) {
-  return kEpiWarps * kStageOutBytes + extra + 1024 /*align slack*/ + 256 /*barriers*/;
+  return kEpiWarps * kStageOutBytes + extra + 1024 /*align slack*/ + 512 /*barriers*/;
 }
 __host__ inline int gemm_max_stages(const GemmGeom& g, int extra = 0) {
   int s = (kGemmSmemLimit - gemm_fixed_smem_bytes(extra)) / gemm_stage_bytes(g);
   return s > 8 ? 8 : s;
 }
+// halo mode: A ring fixed at 2 stages, the rest goes to the weights ring (0 if it does not fit)
+__host__ inline int gemm_halo_b_stages(const GemmGeom& g, int a_stages = 2) {
+  int s = (kGemmSmemLimit - gemm_fixed_smem_bytes(0) - a_stages * gemm_halo_a_stage_bytes(g)) / gemm_b_stage_bytes(g);
+  return s > 8 ? 8 : s;
+}
 __host__ inline int gemm_smem_bytes(const GemmGeom& g, int extra = 0) {
+  if (g.halo) return g.stages * gemm_halo_a_stage_bytes(g) + g.stages_b * gemm_b_stage_bytes(g) + gemm_fixed_smem_bytes(extra);
   return g.stages * gemm_stage_bytes(g) + gemm_fixed_smem_bytes(extra);
 }
 
@@ -243,8 +263,10 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
   // (pointer arithmetic on smem_raw -- not an integer round-trip -- so the compiler keeps the shared address space and
   //  emits LDS/STS instead of generic LD/ST for everything derived from it)
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int stage_bytes = gemm_stage_bytes(g);
-  uint8_t* out_stage = smem + g.stages * stage_bytes;                           // [kEpiWarps][4 KiB]
+  const int stage_bytes = g.halo ? gemm_halo_a_stage_bytes(g) : gemm_stage_bytes(g);
+  const int b_stage_bytes = gemm_b_stage_bytes(g);                               // halo mode: the weights ring
+  uint8_t* smem_b = smem + g.stages * stage_bytes;                              // [stages_b][nB][block_n x 128 B] (halo mode)
+  uint8_t* out_stage = smem_b + (g.halo ? g.stages_b * b_stage_bytes : 0);     // [kEpiWarps][4 KiB]
   uint8_t* extra_smem = out_stage + kEpiWarps * kStageOutBytes;                 // [Epi::kExtraSmemBytes]
   uint64_t* bars = reinterpret_cast<uint64_t*>(extra_smem + Epi::kExtraSmemBytes);
   uint64_t* full_bar = bars;                     // [stages]
@@ -252,6 +274,8 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
   uint64_t* tfull_bar = bars + 2 * g.stages;     // [2]
   uint64_t* tempty_bar = tfull_bar + 2;          // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* bfull_bar = tempty_bar + 3;          // [stages_b]   (halo mode)
+  uint64_t* bempty_bar = bfull_bar + 8;          // [stages_b]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -267,6 +291,11 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], kPair ? 1 : n_peers);   // a slot is free when every consumer of my slices has released it
     }
+    if (g.halo)
+      for (int s = 0; s < g.stages_b; ++s) {
+        ptx::mbar_init(&bfull_bar[s], 1);
+        ptx::mbar_init(&bempty_bar[s], 1);
+      }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(&tfull_bar[b], 1);
       ptx::mbar_init(&tempty_bar[b], (kPair ? 2 : 1) * kEpiWarps * 32);   // pair: both CTAs' epilogues release the leader's
@@ -302,7 +331,40 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
 
   if (warp == 0) {
     // ===================================================== TMA producer
-    if (lane == 0) {
+    if (lane == 0 && g.halo) {
+      // ---- halo mode: units (tile, channel block) in sequence; the halo patch of unit u+1 is requested while the taps of
+      // unit u are still streaming (after its second tap), the nine weight tiles of a unit follow one another
+      int sa = 0, sbi = 0;
+      uint32_t pha = 0, phb = 0;
+      auto issue_a = [&](const TileCoord& t, int cb) {
+        ptx::mbar_wait(&empty_bar[sa], pha ^ 1u);
+        ptx::mbar_expect_tx(&full_bar[sa], static_cast<uint32_t>(g.nA * kHaloBytes));
+        for (int i = 0; i < g.nA; ++i)
+          ptx::tma_load_4d(smem + sa * stage_bytes + i * kHaloPieceBytes, &maps.a[i], &full_bar[sa], cb * kBlockK, t.w0 - 1,
+                           t.h0 - 1, t.n0);
+        if (++sa == g.stages) { sa = 0; pha ^= 1u; }
+      };
+      int ti = 0, cb = 0;
+      TileCoord tc;
+      bool valid = tile_at(g, 0, &tc);
+      if (valid) issue_a(tc, 0);
+      while (valid) {
+        int nti = ti, ncb = cb + 1;
+        TileCoord ntc = tc;
+        bool nvalid = true;
+        if (ncb == g.cin_blocks) { ncb = 0; ++nti; nvalid = tile_at(g, nti, &ntc); }
+        for (int tap = 0; tap < 9; ++tap) {
+          if (tap == 2 && nvalid) issue_a(ntc, ncb);
+          ptx::mbar_wait(&bempty_bar[sbi], phb ^ 1u);
+          ptx::mbar_expect_tx(&bfull_bar[sbi], static_cast<uint32_t>(b_stage_bytes));
+          for (int i = 0; i < g.nB; ++i)
+            ptx::tma_load_2d(smem_b + sbi * b_stage_bytes + i * g.block_n * kBlockK * 2, &maps.b[i], &bfull_bar[sbi],
+                             (tap * g.cin_blocks + cb) * kBlockK, tc.n_tile * g.block_n);
+          if (++sbi == g.stages_b) { sbi = 0; phb ^= 1u; }
+        }
+        ti = nti; cb = ncb; tc = ntc; valid = nvalid;
+      }
+    } else if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx_bytes = static_cast<uint32_t>(stage_bytes);
@@ -407,7 +469,45 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
       int acc = 0;
       uint32_t acc_phase = 0;
       TileCoord tc_unused;
-      for (int ti = 0; tile_at(g, ti, &tc_unused); ++ti) {
+      int sbi = 0;
+      uint32_t phb = 0;
+      for (int ti = 0; g.halo && tile_at(g, ti, &tc_unused); ++ti) {
+        // ---- halo mode: per channel block one halo patch, nine taps = nine start rows into it
+        ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * g.n_acc * g.block_n);
+        uint32_t started = 0;
+        for (int cb = 0; cb < g.cin_blocks; ++cb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          const uint32_t sa = ptx::smem_u32(smem + stage * stage_bytes);
+          for (int tap = 0; tap < 9; ++tap) {
+            ptx::mbar_wait(&bfull_bar[sbi], phb);
+            ptx::tc_fence_after();
+            const uint32_t sb = ptx::smem_u32(smem_b + sbi * b_stage_bytes);
+            const uint32_t a_off = static_cast<uint32_t>(((tap / 3) * kHaloPW + (tap % 3)) * kBlockK * 2);
+            for (int i = 0; i < g.n_mma; ++i) {
+              const uint64_t adesc = ptx::make_kmajor_sw128_desc_sbo(sa + g.mma_a[i] * kHaloPieceBytes + a_off,
+                                                                     kHaloPW * kBlockK * 2);
+              const uint64_t bdesc = ptx::make_kmajor_sw128_desc(sb + g.mma_b[i] * g.block_n * kBlockK * 2);
+              const uint32_t a_id = static_cast<uint32_t>(g.mma_acc[i]);
+              const uint32_t d_acc = d_tmem + a_id * static_cast<uint32_t>(g.block_n);
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k) {
+                ptx::umma_f16(d_acc, adesc + 2u * k, bdesc + 2u * k, idesc, (started >> a_id) & 1u);
+                started |= 1u << a_id;
+              }
+            }
+            ptx::umma_commit(&bempty_bar[sbi]);
+            if (++sbi == g.stages_b) { sbi = 0; phb ^= 1u; }
+          }
+          ptx::umma_commit(&empty_bar[stage]);       // the halo patch may be overwritten once these MMAs have read it
+          if (++stage == g.stages) { stage = 0; phase ^= 1u; }
+        }
+        ptx::umma_commit(&tfull_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+      for (int ti = 0; !g.halo && tile_at(g, ti, &tc_unused); ++ti) {
         ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * g.n_acc * g.block_n);

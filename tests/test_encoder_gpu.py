@@ -126,6 +126,35 @@ def test_cta_pair_mode_is_bit_identical(sd, cuda_device, monkeypatch):
     assert torch.equal(base[0], pair[0]) and torch.equal(base[1], pair[1])
 
 
+@pytest.mark.parametrize("precision,tol", [("fp16x2", 5e-5), ("bf16", 2e-2)])
+def test_halo_mode_matches_oracle(sd, ref5, cuda_device, monkeypatch, precision, tol):
+    """DAD3D_HALO=1: the 3x3 stride-1 layers run on 8x16-pixel tiles whose nine taps read one shared halo patch through
+    shifted UMMA descriptors (k order: channel block outer, tap inner -- not bit-identical to the default path)."""
+    from dad_3dheads_b200.encoder import Dad3dEncoder, fold_state_dict
+    from tests.folded_ref import run_folded
+    monkeypatch.setenv("DAD3D_HALO", "1")
+    x, ref = ref5
+    enc = Dad3dEncoder(sd, cuda_device, precision=precision)
+    out = enc(x.to(cuda_device))
+    errs = {k: _rel(out[k], ref[k]) for k in ref}
+    if precision == "fp16x2":                      # localise a failure to the layer
+        x2 = torch.randn(2, 3, 256, 256, generator=torch.Generator().manual_seed(7))
+        layers, fw = fold_state_dict(sd)
+        with torch.no_grad():
+            lref = run_folded(x2, layers, fw)
+        enc.set_debug(True)
+        enc.forward_raw(x2.to(cuda_device))
+        bad = {}
+        for name in ("s1u1c2", "s2u1c2", "s2u2c2", "s3u1c2", "s3u2c2", "heat"):
+            a = enc.read_activation(name)
+            r = lref[name]
+            e = _rel(a[..., : r.shape[1]].permute(0, 3, 1, 2), r)
+            if e > 5e-5:
+                bad[name] = e
+        assert not bad, bad
+    assert all(e < tol for e in errs.values()), errs
+
+
 def test_encoder_golden_fixture(sd, cuda_device):
     """tests/golden/encoder_golden.npz (tools/make_golden.py: fp64 oracle, weight seed 0, image seed 777)."""
     import os
