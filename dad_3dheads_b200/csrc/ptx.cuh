@@ -143,6 +143,20 @@ __device__ __forceinline__ uint32_t mapa_u32(const void* local, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
+// One lane of the (fully converged) warp: the idiom the compiler recognises for single-thread tcgen05 / TMA issue.  Code that
+// gates on `lane == 0` instead makes every operand thread-private, and each UTCHMMA / UTMALDG is then wrapped in an
+// ELECT + BRA.U.ANY uniformisation loop (~100 cycles per instruction, measured as the limiter of the whole engine).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 // thread-block cluster helpers
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

@@ -277,7 +277,7 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
   uint64_t* bfull_bar = tempty_bar + 3;          // [stages_b]   (halo mode)
   uint64_t* bempty_bar = bfull_bar + 8;          // [stages_b]
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);   // provably warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
   const int num_kb = g.R * g.S * g.cin_blocks;
 
@@ -331,17 +331,22 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
 
   if (warp == 0) {
     // ===================================================== TMA producer
-    if (lane == 0 && g.halo) {
+    // The WHOLE warp walks the schedule (all control flow and operands stay warp-uniform -> uniform registers); one elected
+    // lane issues the TMA instructions.
+    if (g.halo) {
       // ---- halo mode: units (tile, channel block) in sequence; the halo patch of unit u+1 is requested while the taps of
       // unit u are still streaming (after its second tap), the nine weight tiles of a unit follow one another
       int sa = 0, sbi = 0;
       uint32_t pha = 0, phb = 0;
       auto issue_a = [&](const TileCoord& t, int cb) {
         ptx::mbar_wait(&empty_bar[sa], pha ^ 1u);
-        ptx::mbar_expect_tx(&full_bar[sa], static_cast<uint32_t>(g.nA * kHaloBytes));
-        for (int i = 0; i < g.nA; ++i)
-          ptx::tma_load_4d(smem + sa * stage_bytes + i * kHaloPieceBytes, &maps.a[i], &full_bar[sa], cb * kBlockK, t.w0 - 1,
-                           t.h0 - 1, t.n0);
+        if (ptx::elect_one_sync()) {
+          ptx::mbar_expect_tx(&full_bar[sa], static_cast<uint32_t>(g.nA * kHaloBytes));
+          for (int i = 0; i < g.nA; ++i)
+            ptx::tma_load_4d(smem + sa * stage_bytes + i * kHaloPieceBytes, &maps.a[i], &full_bar[sa], cb * kBlockK, t.w0 - 1,
+                             t.h0 - 1, t.n0);
+        }
+        __syncwarp();
         if (++sa == g.stages) { sa = 0; pha ^= 1u; }
       };
       int ti = 0, cb = 0;
@@ -356,15 +361,18 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
         for (int tap = 0; tap < 9; ++tap) {
           if (tap == 2 && nvalid) issue_a(ntc, ncb);
           ptx::mbar_wait(&bempty_bar[sbi], phb ^ 1u);
-          ptx::mbar_expect_tx(&bfull_bar[sbi], static_cast<uint32_t>(b_stage_bytes));
-          for (int i = 0; i < g.nB; ++i)
-            ptx::tma_load_2d(smem_b + sbi * b_stage_bytes + i * g.block_n * kBlockK * 2, &maps.b[i], &bfull_bar[sbi],
-                             (tap * g.cin_blocks + cb) * kBlockK, tc.n_tile * g.block_n);
+          if (ptx::elect_one_sync()) {
+            ptx::mbar_expect_tx(&bfull_bar[sbi], static_cast<uint32_t>(b_stage_bytes));
+            for (int i = 0; i < g.nB; ++i)
+              ptx::tma_load_2d(smem_b + sbi * b_stage_bytes + i * g.block_n * kBlockK * 2, &maps.b[i], &bfull_bar[sbi],
+                               (tap * g.cin_blocks + cb) * kBlockK, tc.n_tile * g.block_n);
+          }
+          __syncwarp();
           if (++sbi == g.stages_b) { sbi = 0; phb ^= 1u; }
         }
         ti = nti; cb = ncb; tc = ntc; valid = nvalid;
       }
-    } else if (lane == 0) {
+    } else {
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx_bytes = static_cast<uint32_t>(stage_bytes);
@@ -375,6 +383,7 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
             uint8_t* st = smem + stage * stage_bytes;
             const int r = kb - num_kb;
+            if (ptx::elect_one_sync()) {
             if constexpr (kPair) {
               // CTA pair: my A tile and my half of the B rows; every byte of both CTAs is accounted on the leader's barrier
               const uint32_t lead_full = ptx::mapa_u32(&full_bar[stage], 0);
@@ -416,6 +425,8 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
                 ptx::tma_load_2d(sb2 + i * g.block_n * kBlockK * 2, &maps.b[i], &full_bar[stage], (num_kb + r) * kBlockK,
                                  tc.n_tile * g.block_n);
             }
+            }
+            __syncwarp();
             if (++stage == g.stages) { stage = 0; phase ^= 1u; }
             continue;
           }
@@ -424,13 +435,14 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
           const int r = tap / g.S;
           const int s = tap - r * g.S;
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
-          if (!kPair) ptx::mbar_expect_tx(&full_bar[stage], tx_bytes);
-          else if (crank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * tx_bytes);
           uint8_t* st = smem + stage * stage_bytes;
           const int cw = tc.w0 * g.stride + s - g.pad_w;
           const int ch = tc.h0 * g.stride + r - g.pad_h;
           uint8_t* sb = st + g.nA * kTileABytes;
           const int kcol = kb * kBlockK;
+          if (ptx::elect_one_sync()) {
+          if (!kPair) ptx::mbar_expect_tx(&full_bar[stage], tx_bytes);
+          else if (crank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * tx_bytes);
           if constexpr (kPair) {
             const uint32_t lead_full = ptx::mapa_u32(&full_bar[stage], 0);
             const int b_half = (g.block_n >> 1) * kBlockK * 2;
@@ -455,13 +467,15 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
               ptx::tma_load_2d_mc(sb + i * g.block_n * kBlockK * 2 + ci * b_rows * kBlockK * 2, &maps.b[i],
                                   &full_bar[stage], kcol, tc.n_tile * g.block_n + ci * b_rows, mask_b);
           }
+          }
+          __syncwarp();
           if (++stage == g.stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================================================== MMA issuer (single thread)
-    if (lane == 0 && (!kPair || crank == 0)) {
+    // ===================================================== MMA issuer (whole warp walks the schedule, one elected lane issues)
+    if (!kPair || crank == 0) {
       const uint32_t idesc = ptx::make_idesc_f16(g.fmt16, kPair ? 2 * kBlockM : kBlockM, static_cast<uint32_t>(g.block_n));
       const int b_piece_bytes = (g.block_n >> (kPair ? 1 : 0)) * kBlockK * 2;
       int stage = 0;
@@ -491,19 +505,25 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
               const uint64_t bdesc = ptx::make_kmajor_sw128_desc(sb + g.mma_b[i] * g.block_n * kBlockK * 2);
               const uint32_t a_id = static_cast<uint32_t>(g.mma_acc[i]);
               const uint32_t d_acc = d_tmem + a_id * static_cast<uint32_t>(g.block_n);
+              const uint32_t first = (started >> a_id) & 1u;
+              started |= 1u << a_id;
+              if (ptx::elect_one_sync()) {
 #pragma unroll
-              for (int k = 0; k < kBlockK / 16; ++k) {
-                ptx::umma_f16(d_acc, adesc + 2u * k, bdesc + 2u * k, idesc, (started >> a_id) & 1u);
-                started |= 1u << a_id;
+                for (int k = 0; k < kBlockK / 16; ++k)
+                  ptx::umma_f16(d_acc, adesc + 2u * k, bdesc + 2u * k, idesc, k > 0 ? 1u : first);
               }
+              __syncwarp();
             }
-            ptx::umma_commit(&bempty_bar[sbi]);
+            if (ptx::elect_one_sync()) {
+              ptx::umma_commit(&bempty_bar[sbi]);
+              if (tap == 8) ptx::umma_commit(&empty_bar[stage]);   // the halo patch may be overwritten once these MMAs have read it
+              if (tap == 8 && cb == g.cin_blocks - 1) ptx::umma_commit(&tfull_bar[acc]);
+            }
+            __syncwarp();
             if (++sbi == g.stages_b) { sbi = 0; phb ^= 1u; }
           }
-          ptx::umma_commit(&empty_bar[stage]);       // the halo patch may be overwritten once these MMAs have read it
           if (++stage == g.stages) { stage = 0; phase ^= 1u; }
         }
-        ptx::umma_commit(&tfull_bar[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -526,21 +546,31 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
             const uint64_t bdesc = ptx::make_kmajor_sw128_desc(sb + pb * b_piece_bytes);
             const uint32_t a_id = static_cast<uint32_t>(res_block ? g.mma_res_acc[i] : g.mma_acc[i]);
             const uint32_t d_acc = d_tmem + a_id * static_cast<uint32_t>(g.block_n);
+            const uint32_t first = (started >> a_id) & 1u;     // 0: this accumulator's first MMA of the tile overwrites
+            started |= 1u << a_id;
+            if (ptx::elect_one_sync()) {
 #pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k) {
-              // advancing 16 elements (32 B) along K inside the 128 B swizzle row = +2 in the (addr >> 4) field
-              if constexpr (kPair) ptx::umma_f16_2sm(d_acc, adesc + 2u * k, bdesc + 2u * k, idesc, (started >> a_id) & 1u);
-              else ptx::umma_f16(d_acc, adesc + 2u * k, bdesc + 2u * k, idesc, (started >> a_id) & 1u);
-              started |= 1u << a_id;
+              for (int k = 0; k < kBlockK / 16; ++k) {
+                // advancing 16 elements (32 B) along K inside the 128 B swizzle row = +2 in the (addr >> 4) field
+                if constexpr (kPair) ptx::umma_f16_2sm(d_acc, adesc + 2u * k, bdesc + 2u * k, idesc, k > 0 ? 1u : first);
+                else ptx::umma_f16(d_acc, adesc + 2u * k, bdesc + 2u * k, idesc, k > 0 ? 1u : first);
+              }
+            }
+            __syncwarp();
+          }
+          const bool last_kb = kb == num_kb + g.res_kb - 1;
+          if (ptx::elect_one_sync()) {
+            if constexpr (kPair) ptx::umma_commit_2sm_mc(&empty_bar[stage], 3);   // both CTAs' slots were read by these MMAs
+            else if (csize == 1) ptx::umma_commit(&empty_bar[stage]);   // smem slot reusable once these MMAs have read it
+            else ptx::umma_commit_mc(&empty_bar[stage], mask_peers);   // ... tell every CTA that fills this slot
+            if (last_kb) {
+              if constexpr (kPair) ptx::umma_commit_2sm_mc(&tfull_bar[acc], 3);   // both halves of the accumulator are complete
+              else ptx::umma_commit(&tfull_bar[acc]);   // accumulator complete
             }
           }
-          if constexpr (kPair) ptx::umma_commit_2sm_mc(&empty_bar[stage], 3);   // both CTAs' slots were read by these MMAs
-          else if (csize == 1) ptx::umma_commit(&empty_bar[stage]);   // smem slot reusable once these MMAs have read it
-          else ptx::umma_commit_mc(&empty_bar[stage], mask_peers);   // ... tell every CTA that fills this slot
+          __syncwarp();
           if (++stage == g.stages) { stage = 0; phase ^= 1u; }
         }
-        if constexpr (kPair) ptx::umma_commit_2sm_mc(&tfull_bar[acc], 3);   // both halves of the accumulator are complete
-        else ptx::umma_commit(&tfull_bar[acc]);   // accumulator complete
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
