@@ -122,7 +122,7 @@ struct dad3d_encoder {
   std::unique_ptr<Plan> plan;
   size_t ws_cache_B = 0, ws_cache_bytes = 0;
   bool stem_simt = false;          // env DAD3D_STEM_SIMT=1: run the stem on the fp32 CUDA-core kernel instead of the tile engine
-  bool use_halo = false;           // env DAD3D_HALO=1: halo-reuse tiles for the 3x3 stride-1 layers
+  bool use_halo = true;            // halo-reuse tiles for the 3x3 stride-1 layers (env DAD3D_HALO=0 selects the per-tap path)
   bool use_pair = false;           // env DAD3D_PAIR=1: cta_group::2 CTA pairs for the large 128-wide layers
   bool use_pdl = false;            // programmatic dependent launch for the tile-engine kernels (env DAD3D_PDL=1 enables;
                                    // measured neutral on B200 at batch 64: 6689 vs 6764 heads/s, so off by default)
@@ -683,7 +683,7 @@ int dad3d_encoder_create(dad3d_encoder** out, const dad3d_conv_weights* layers, 
     const char* e = std::getenv("DAD3D_PDL");
     enc->use_pdl = (e && e[0] == '1');
     const char* e4 = std::getenv("DAD3D_HALO");
-    enc->use_halo = (e4 && e4[0] == '1');
+    enc->use_halo = !(e4 && e4[0] == '0');
     const char* e3 = std::getenv("DAD3D_PAIR");
     enc->use_pair = (e3 && e3[0] == '1');
     const char* e2 = std::getenv("DAD3D_STEM_SIMT");

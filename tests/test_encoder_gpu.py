@@ -127,12 +127,14 @@ def test_cta_pair_mode_is_bit_identical(sd, cuda_device, monkeypatch):
 
 
 @pytest.mark.parametrize("precision,tol", [("fp16x2", 5e-5), ("bf16", 2e-2)])
-def test_halo_mode_matches_oracle(sd, ref5, cuda_device, monkeypatch, precision, tol):
-    """DAD3D_HALO=1: the 3x3 stride-1 layers run on 8x16-pixel tiles whose nine taps read one shared halo patch through
-    shifted UMMA descriptors (k order: channel block outer, tap inner -- not bit-identical to the default path)."""
+@pytest.mark.parametrize("halo", ["1", "0"])
+def test_halo_and_per_tap_paths_match_oracle(sd, ref5, cuda_device, monkeypatch, precision, tol, halo):
+    """Default (DAD3D_HALO unset / 1): the 3x3 stride-1 layers run on 8x16-pixel tiles whose nine taps read one shared halo
+    patch through shifted UMMA descriptors (k order: channel block outer, tap inner); DAD3D_HALO=0: one TMA box per tap
+    (tap outer).  Both against the oracle, with the 3x3 layers checked one by one."""
     from dad_3dheads_b200.encoder import Dad3dEncoder, fold_state_dict
     from tests.folded_ref import run_folded
-    monkeypatch.setenv("DAD3D_HALO", "1")
+    monkeypatch.setenv("DAD3D_HALO", halo)
     x, ref = ref5
     enc = Dad3dEncoder(sd, cuda_device, precision=precision)
     out = enc(x.to(cuda_device))
