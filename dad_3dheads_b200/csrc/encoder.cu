@@ -435,6 +435,12 @@ int make_plan(dad3d_encoder* enc, int B, void* ws, size_t ws_bytes, bool layout_
     // "halo mode"); needs a map of at least 8 x 16 pixels and room for a two-deep weights ring (checked below)
     bool halo = enc->use_halo && !s.stem && w->R == 3 && w->S == 3 && s.stride == 1 && s.pad == 1 && Wo >= kHaloTW &&
                 Ho >= kHaloTH;
+    if (halo) {                                       // two halo patches + at least two weight tiles must fit (bf16x3 at N = 128 does not)
+      GemmGeom probe;
+      std::memset(&probe, 0, sizeof(probe));
+      probe.nA = enc->P; probe.nB = enc->P; probe.block_n = w->block_n;
+      halo = gemm_halo_b_stages(probe) >= 2;
+    }
     if (halo) { g.tw = kHaloTW; g.th = kHaloTH; g.tn = 1; }
     g.tiles_w = ceil_div(Wo, g.tw);
     g.tiles_h = ceil_div(Ho, g.th);
