@@ -500,7 +500,7 @@ int make_plan(dad3d_encoder* enc, int B, void* ws, size_t ws_bytes, bool layout_
       const uint32_t es[4] = {1, static_cast<uint32_t>(s.stride), static_cast<uint32_t>(s.stride), 1};
       const uint16_t* basep = reinterpret_cast<const uint16_t*>(ti.ptr) + static_cast<size_t>(p) * ti.plane_elems();
       if (!make_tmap_16bit(&s.maps.a[p], basep, 4, dims, strides, box, es)) return DAD3D_ERR_CUDA;
-      s.maps.b[p] = (narrow || pair) ? w->map_b64[p] : w->map_b[p];    // pair: each CTA loads a 64-row half of the B tile
+      s.maps.b[p] = (narrow || g.pair) ? w->map_b64[p] : w->map_b[p];    // pair: each CTA loads a 64-row half of the B tile
     }
     if (res_in_k || src2) {
       const TensorInfo& tr = plan->tensors[s.res];
