@@ -38,7 +38,12 @@ def _traffic_from_profile():
     """DRAM bytes per launch of the dominant kernel, from the committed ncu launch list of this same command
     (profiles/r01_step_summary_*.json, written by tools/summarize_launches.py).  None when no capture is committed."""
     import glob
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_step_summary_*.json")))
+    import re
+
+    def ver(f):                                   # r01_step_summary_v11.json -> (1, 11): newest round, newest version
+        m = re.search(r"r(\d+)_step_summary_v(\d+)\.json$", f)
+        return (int(m.group(1)), int(m.group(2))) if m else (0, 0)
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_step_summary_*.json")), key=ver)
     if not files:
         return None, None
     d = json.load(open(files[-1]))
@@ -195,6 +200,8 @@ def run_ours(args):
         torch.cuda.current_stream().synchronize()                      # the caller holds host results
         return out
 
+    algo_bytes = {}
+
     def timed(fn, steps, profile=False):
         if distributed:
             dist.barrier()
@@ -208,6 +215,9 @@ def run_ours(args):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
+        if profile:
+            lay = pred.model.profile_layers()          # per-launch records (algorithmic bytes), before the window is cleared
+            algo_bytes["per_launch"] = sum(l["bytes"] for l in lay) / max(len(lay), 1)
         prof = pred.model.profile_read() if profile else None
         if profile:
             pred.model.set_profile(False)
@@ -283,8 +293,8 @@ def run_ours(args):
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
                          "traffic": traffic if B == PER_GPU_BATCH and args.precision == "fp16x2" else None,
                          "traffic_unit": "DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, averaged "
-                                         "over the 77 tile-engine launches of one step)", "traffic_source": traffic_src,
-                         "algorithmic_bytes_per_launch": None,
+                                         "over the tile-engine launches of one step)", "traffic_source": traffic_src,
+                         "algorithmic_bytes_per_launch": algo_bytes.get("per_launch"),
                          "peak_source": peaks["source"] + " bf16 dense, sustained",
                          "products_per_mac": products, "executed_tflops": achieved * products,
                          "frac_executed": achieved * products / peak if peak else None,
