@@ -266,9 +266,12 @@ struct EpiConvT {
       for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
     }
     const int swz = (c.lane >> 1) & 3;
-    uint8_t* rowp = c.stage + c.lane * 64;
     for (int p = 0; p < ep.out_planes; ++p) {
-      if (c.lane == 0) ptx::bulk_wait_read0();        // previous store has finished reading the staging tile
+      // the warp's 4 KiB staging area holds two 2 KiB store tiles used alternately: only the store before the previous one
+      // has to have finished reading its tile
+      uint8_t* tile = c.stage + ((c.store_seq++ & 1) << 11);
+      uint8_t* rowp = tile + c.lane * 64;
+      if (c.lane == 0) ptx::bulk_wait_read1();
       __syncwarp();
 #pragma unroll
       for (int q = 0; q < 4; ++q) {                   // 16-byte chunks of this row
@@ -283,9 +286,9 @@ struct EpiConvT {
         if (ep.up2) {
           const int row0 = c.bn0 * c.g->Ho + c.bh0;   // merged (image, row) coordinate of the 5-D parity view
 #pragma unroll
-          for (int ab = 0; ab < 4; ++ab) ptx::tma_store_5d(&c.maps->c[p], c.stage, col, ab & 1, c.bw0, ab >> 1, row0);
+          for (int ab = 0; ab < 4; ++ab) ptx::tma_store_5d(&c.maps->c[p], tile, col, ab & 1, c.bw0, ab >> 1, row0);
         } else {
-          ptx::tma_store_4d(&c.maps->c[p], c.stage, col, c.bw0, c.bh0, c.bn0);
+          ptx::tma_store_4d(&c.maps->c[p], tile, col, c.bw0, c.bh0, c.bn0);
         }
         ptx::bulk_commit();
       }

@@ -192,6 +192,7 @@ struct EpiCtx {
   uint8_t* stage;    // warp-private 4 KiB staging tile (1024-byte aligned)
   uint8_t* extra;    // Epi::kExtraSmemBytes of CTA-wide shared memory (epilogue-specific use)
   int prev_m_tile;   // row tile of the previous tile this CTA processed (-1 for the first)
+  mutable int store_seq;   // number of TMA stores this warp has issued (epilogues alternating between two staging tiles)
   uint64_t* tempty;  // arrive here (every epilogue thread, once) when the accumulator has been drained into registers
   uint32_t tempty_cluster;   // CTA-pair mode: shared::cluster address of the LEADER's tmem-empty barrier (0 = use tempty)
   // this thread's accumulator row
@@ -587,6 +588,7 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
     c.stage = out_stage + (warp - kFirstEpiWarp) * kStageOutBytes;
     c.extra = extra_smem;
     c.prev_m_tile = -1;
+    c.store_seq = 0;
     const int row = c.wq * 32 + lane;
     const int iw = row % g.tw;
     const int ih = (row / g.tw) % g.th;
