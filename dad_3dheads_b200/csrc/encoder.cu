@@ -213,7 +213,7 @@ int build_graph(Builder& b) {
   const int B = b.B;
   Plan* plan = b.plan;
   // ---- stem: conv7x7/2 + BN + ReLU (fp32 SIMT) -> maxpool 3x3/2 -> pieces [B,64,64,64]
-  const int t_stem = b.tensor(B, kImg / 2, kImg / 2, 64, true);
+  const int t_stem = b.tensor(B, kImg / 2, kImg / 2, 64, /*f32=*/b.enc->stem_simt);   // tensor-core stem: piece planes
   if (b.enc->stem_simt) {
     Step s; s.kind = kStemConv; s.out_f32 = t_stem; std::memset(&s.maps, 0, sizeof(s.maps));
     b.push(s);
@@ -233,7 +233,7 @@ int build_graph(Builder& b) {
     s.w = b.W("stem");
     s.stem = 1;
     s.relu = 1;
-    s.out_f32 = t_stem;
+    s.out = t_stem;
     b.push(s);
   }
   plan->tensors[t_stem].name = "stem_conv";
@@ -901,9 +901,11 @@ int dad3d_encoder_forward(dad3d_encoder* enc, const float* images_d, int32_t B, 
         const TensorInfo& ti = T(s.in);
         const TensorInfo& to = T(s.out);
         const long long total = static_cast<long long>(B) * to.H * to.W * 8;
+        ActView pieces{nullptr, 0, 0, 0, enc->fp16};
+        if (!ti.f32) pieces = view(s.in);
         stem_pool_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
-            reinterpret_cast<const float*>(ti.ptr), B, ti.H, ti.W, reinterpret_cast<uint16_t*>(to.ptr), to.plane_elems(),
-            to.planes, enc->fp16);
+            reinterpret_cast<const float*>(ti.ptr), pieces, B, ti.H, ti.W, reinterpret_cast<uint16_t*>(to.ptr),
+            to.plane_elems(), to.planes, enc->fp16);
         count_launch();
         break;
       }

@@ -430,8 +430,9 @@ __global__ void stem_s2d_kernel(const float* __restrict__ img, int B, int H, int
 }
 
 // MaxPool2d(3, stride 2, pad 1) over NHWC fp32 [B,Hi,Wi,64] -> pieces [B,Hi/2,Wi/2,64].  thread = 8 channels of a pixel.
-__global__ void stem_pool_kernel(const float* __restrict__ in, int B, int Hi, int Wi, uint16_t* __restrict__ out,
-                                 long long out_plane, int planes, int fp16) {
+// `in` is fp32 NHWC (SIMT stem) when in_pieces.base == nullptr, otherwise the piece tensor written by the tensor-core stem.
+__global__ void stem_pool_kernel(const float* __restrict__ in, ActView in_pieces, int B, int Hi, int Wi,
+                                 uint16_t* __restrict__ out, long long out_plane, int planes, int fp16) {
   const int Ho = Hi / 2, Wo = Wi / 2;
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long total = static_cast<long long>(B) * Ho * Wo * 8;
@@ -450,7 +451,15 @@ __global__ void stem_pool_kernel(const float* __restrict__ in, int B, int Hi, in
     for (int dx = -1; dx <= 1; ++dx) {
       const int ix = ox * 2 + dx;
       if (ix < 0 || ix >= Wi) continue;
-      const float4* s = reinterpret_cast<const float4*>(in + ((b * Hi + iy) * Wi + ix) * 64 + cg * 8);
+      const long long off = ((b * Hi + iy) * Wi + ix) * 64 + cg * 8;
+      if (in_pieces.base != nullptr) {
+        float v[8];
+        act_load8(in_pieces, off, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], v[j]);
+        continue;
+      }
+      const float4* s = reinterpret_cast<const float4*>(in + off);
       const float4 a = __ldg(s), c = __ldg(s + 1);
       m[0] = fmaxf(m[0], a.x); m[1] = fmaxf(m[1], a.y); m[2] = fmaxf(m[2], a.z); m[3] = fmaxf(m[3], a.w);
       m[4] = fmaxf(m[4], c.x); m[5] = fmaxf(m[5], c.y); m[6] = fmaxf(m[6], c.z); m[7] = fmaxf(m[7], c.w);
