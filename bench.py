@@ -362,7 +362,7 @@ def run_decode_microbench(args):
 
     def step():
         for lo, hi in passes:
-            dec.decode(params[lo:hi], want_vertices=True, want_projected=False, fast=fast)
+            dec.decode(params[lo:hi], want_vertices=True, want_projected=False, fast=fast, cluster=args.decode_cluster)
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -450,6 +450,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="images per GPU per step")
+    ap.add_argument("--decode-cluster", action="store_true", help="decode microbench: 2x2 multicast clusters (A/B only)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-strict", action="store_true", help="skip the strict-operand comparison run")
     ap.add_argument("--precision", default="fp16x2", choices=["fp32", "bf16x3", "fp16x2", "bf16x2", "fp16", "bf16"])

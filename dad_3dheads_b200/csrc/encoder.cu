@@ -123,6 +123,7 @@ struct dad3d_encoder {
   size_t ws_cache_B = 0, ws_cache_bytes = 0;
   bool stem_simt = false;          // env DAD3D_STEM_SIMT=1: run the stem on the fp32 CUDA-core kernel instead of the tile engine
   bool use_halo = true;            // halo-reuse tiles for the 3x3 stride-1 layers (env DAD3D_HALO=0 selects the per-tap path)
+  int halo_cluster = 1;            // env DAD3D_HALO_CLUSTER=2: halo layers run as clusters of 2 row tiles that multicast the weights
   bool use_pair = false;           // env DAD3D_PAIR=1: cta_group::2 CTA pairs for the large 128-wide layers
   bool use_pdl = false;            // programmatic dependent launch for the tile-engine kernels (env DAD3D_PDL=1 enables;
                                    // measured neutral on B200 at batch 64: 6689 vs 6764 heads/s, so off by default)
@@ -483,6 +484,10 @@ int make_plan(dad3d_encoder* enc, int B, void* ws, size_t ws_bytes, bool layout_
     g.stages = gemm_max_stages(g);
     if (halo) {
       g.halo = 1;
+      if (enc->halo_cluster == 2 && block_n == 128 && w->has_b64 && m_tiles >= 2 * enc->num_sms) {
+        g.cl_m = 2;                                   // two row tiles share every weight tile (each loads half, multicast)
+        g.sched = 1;
+      }
       g.stages = 2;
       g.stages_b = gemm_halo_b_stages(g);
       if (g.stages_b < 2) { set_error("layer " + w->name + ": halo pipeline does not fit shared memory"); return DAD3D_ERR_INVALID; }
@@ -500,7 +505,7 @@ int make_plan(dad3d_encoder* enc, int B, void* ws, size_t ws_bytes, bool layout_
       const uint32_t es[4] = {1, static_cast<uint32_t>(s.stride), static_cast<uint32_t>(s.stride), 1};
       const uint16_t* basep = reinterpret_cast<const uint16_t*>(ti.ptr) + static_cast<size_t>(p) * ti.plane_elems();
       if (!make_tmap_16bit(&s.maps.a[p], basep, 4, dims, strides, box, es)) return DAD3D_ERR_CUDA;
-      s.maps.b[p] = (narrow || g.pair) ? w->map_b64[p] : w->map_b[p];    // pair: each CTA loads a 64-row half of the B tile
+      s.maps.b[p] = (narrow || g.pair || g.cl_m == 2) ? w->map_b64[p] : w->map_b[p];    // pair: each CTA loads a 64-row half of the B tile
     }
     if (res_in_k || src2) {
       const TensorInfo& tr = plan->tensors[s.res];
@@ -598,7 +603,9 @@ int launch_conv(dad3d_encoder* enc, const Step& s, cudaStream_t stream) {
   const GemmGeom& g = s.geom;
   const int m_tiles_total = g.tiles_w * g.tiles_h * g.tiles_n;
   const int total = g.pair ? ((m_tiles_total + 1) / 2) * g.n_tiles * 2 : m_tiles_total * g.n_tiles;
-  const int grid = g.pair ? std::min(total, enc->num_sms & ~1) : std::min(total, enc->num_sms);
+  int grid = g.pair ? std::min(total, enc->num_sms & ~1) : std::min(total, enc->num_sms);
+  const int csz = g.pair ? 2 : g.cl_m * g.cl_n;
+  if (!g.pair && csz > 1) grid = std::min(((m_tiles_total + g.cl_m - 1) / g.cl_m) * csz, (enc->num_sms / csz) * csz);
   std::pair<cudaEvent_t, cudaEvent_t>* ev = nullptr;
   if (enc->profile) {
     if (enc->prof_used == enc->prof_events.size()) {
@@ -626,9 +633,9 @@ int launch_conv(dad3d_encoder* enc, const Step& s, cudaStream_t stream) {
       attr[na].val.programmaticStreamSerializationAllowed = 1;
       ++na;
     }
-    if (g.pair) {
+    if (csz > 1) {
       attr[na].id = cudaLaunchAttributeClusterDimension;
-      attr[na].val.clusterDim.x = 2;
+      attr[na].val.clusterDim.x = static_cast<unsigned>(csz);
       attr[na].val.clusterDim.y = 1;
       attr[na].val.clusterDim.z = 1;
       ++na;
@@ -690,6 +697,8 @@ int dad3d_encoder_create(dad3d_encoder** out, const dad3d_conv_weights* layers, 
     enc->use_pdl = (e && e[0] == '1');
     const char* e4 = std::getenv("DAD3D_HALO");
     enc->use_halo = !(e4 && e4[0] == '0');
+    const char* e5 = std::getenv("DAD3D_HALO_CLUSTER");
+    enc->halo_cluster = (e5 && e5[0] == '2') ? 2 : 1;
     const char* e3 = std::getenv("DAD3D_PAIR");
     enc->use_pair = (e3 && e3[0] == '1');
     const char* e2 = std::getenv("DAD3D_STEM_SIMT");

@@ -290,12 +290,13 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
     const int n_peers = g.cl_m + g.cl_n - 1;       // CTAs that read what I multicast == CTAs that multicast to me
     for (int s = 0; s < g.stages; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
-      ptx::mbar_init(&empty_bar[s], kPair ? 1 : n_peers);   // a slot is free when every consumer of my slices has released it
+      ptx::mbar_init(&empty_bar[s], (kPair || g.halo) ? 1 : n_peers);   // a slot is free when every consumer of my slices has
+                                                                        // released it (halo patches are never shared)
     }
     if (g.halo)
       for (int s = 0; s < g.stages_b; ++s) {
         ptx::mbar_init(&bfull_bar[s], 1);
-        ptx::mbar_init(&bempty_bar[s], 1);
+        ptx::mbar_init(&bempty_bar[s], g.cl_m);     // cluster: every CTA that I multicast weight slices to must release the slot
       }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(&tfull_bar[b], 1);
@@ -364,9 +365,18 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
           ptx::mbar_wait(&bempty_bar[sbi], phb ^ 1u);
           if (ptx::elect_one_sync()) {
             ptx::mbar_expect_tx(&bfull_bar[sbi], static_cast<uint32_t>(b_stage_bytes));
-            for (int i = 0; i < g.nB; ++i)
-              ptx::tma_load_2d(smem_b + sbi * b_stage_bytes + i * g.block_n * kBlockK * 2, &maps.b[i], &bfull_bar[sbi],
-                               (tap * g.cin_blocks + cb) * kBlockK, tc.n_tile * g.block_n);
+            if (csize == 1) {
+              for (int i = 0; i < g.nB; ++i)
+                ptx::tma_load_2d(smem_b + sbi * b_stage_bytes + i * g.block_n * kBlockK * 2, &maps.b[i], &bfull_bar[sbi],
+                                 (tap * g.cin_blocks + cb) * kBlockK, tc.n_tile * g.block_n);
+            } else {
+              // cluster of cl_m row tiles sharing the column tile: I fetch 1/cl_m of the weight rows and multicast them
+              const int b_rows = g.block_n / g.cl_m;
+              for (int i = 0; i < g.nB; ++i)
+                ptx::tma_load_2d_mc(smem_b + sbi * b_stage_bytes + i * g.block_n * kBlockK * 2 + ci * b_rows * kBlockK * 2,
+                                    &maps.b[i], &bfull_bar[sbi], (tap * g.cin_blocks + cb) * kBlockK,
+                                    tc.n_tile * g.block_n + ci * b_rows, mask_b);
+            }
           }
           __syncwarp();
           if (++sbi == g.stages_b) { sbi = 0; phb ^= 1u; }
@@ -516,7 +526,8 @@ tile_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmGeom g, const 
               __syncwarp();
             }
             if (ptx::elect_one_sync()) {
-              ptx::umma_commit(&bempty_bar[sbi]);
+              if (csize == 1) ptx::umma_commit(&bempty_bar[sbi]);
+              else ptx::umma_commit_mc(&bempty_bar[sbi], mask_b);     // every CTA that writes into my slot
               if (tap == 8) ptx::umma_commit(&empty_bar[stage]);   // the halo patch may be overwritten once these MMAs have read it
               if (tap == 8 && cb == g.cin_blocks - 1) ptx::umma_commit(&tfull_bar[acc]);
             }
