@@ -84,3 +84,18 @@ def test_graph_replay_equals_eager(predictor, cuda_device):
             torch.cuda.synchronize()
             for k in want:
                 assert torch.equal(got[k], want[k]), k
+
+
+def test_config2_batch_512_bf16_encoder(cuda_device):
+    """BASELINE configs[2]: batch 512, bf16 encoder, fp32-class FLAME decode + 445-landmark projection.  Size-independent
+    checks: finite everywhere, and (eval-mode network: images are independent) a sub-batch run on its own reproduces the
+    corresponding rows bit for bit."""
+    from dad_3dheads_b200.predictor import FaceMeshPredictor
+    pred = FaceMeshPredictor.dad_3dnet(state_dict=synthetic_state_dict(0), precision="bf16")
+    x = torch.randn(512, 3, 256, 256, generator=torch.Generator().manual_seed(512))
+    out = {k: v.clone() for k, v in pred.predict_batch(x, landmark_subset="445").items()}
+    assert out["3d_vertices"].shape == (512, 5023, 3) and out["landmarks_445"].shape == (512, 445, 2)
+    assert all(torch.isfinite(v).all() for v in out.values())
+    sub = pred.predict_batch(x[300:364], landmark_subset="445")
+    for k in out:
+        assert torch.equal(out[k][300:364], sub[k]), k
