@@ -193,6 +193,9 @@ def run_ours(args):
 
     def step_e2e():
         out = run(x_host, landmark_subset=subset)                      # H2D of the raw frames + pre-processing happen in here
+        if distributed:                                                # the same exchange step as the device-resident arm
+            from dad_3dheads_b200.distributed import all_gather_outputs
+            all_gather_outputs(out, ("3dmm_params", "3d_vertices", "landmarks_445"), gathered)
         for k in ("3dmm_params", "points", "3d_vertices", "landmarks_445"):
             if k not in host_out:
                 host_out[k] = torch.empty(out[k].shape, dtype=out[k].dtype).pin_memory()
