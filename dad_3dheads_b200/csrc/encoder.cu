@@ -929,8 +929,9 @@ int dad3d_encoder_forward(dad3d_encoder* enc, const float* images_d, int32_t B, 
         FuseSrc f1{view(s.in2), T(s.in2).H, T(s.in2).W, s.fw[1]};
         FuseSrc f2 = f1;
         if (s.nsrc == 3) f2 = FuseSrc{view(s.in3), T(s.in3).H, T(s.in3).W, s.fw[2]};
-        const long long total = static_cast<long long>(to.N) * to.H * to.W * (to.C / 8);
-        bifpn_fuse_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+        const dim3 fgrid(static_cast<unsigned>(ceil_div(to.W * (to.C / 8), 256)), static_cast<unsigned>(to.H),
+                         static_cast<unsigned>(to.N));
+        bifpn_fuse_kernel<<<fgrid, 256, 0, stream>>>(
             f0, f1, f2, s.nsrc, to.N, to.H, to.W, to.C, reinterpret_cast<uint16_t*>(to.ptr), to.plane_elems(), to.planes,
             enc->fp16);
         count_launch();
@@ -939,8 +940,9 @@ int dad3d_encoder_forward(dad3d_encoder* enc, const float* images_d, int32_t B, 
       case kConcat: {
         const TensorInfo& to = T(s.out);
         const TensorInfo& th = T(s.in2);
-        const long long total = static_cast<long long>(to.N) * to.H * to.W * (to.C / 8);
-        fusion_concat_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+        const int cthreads = ceil_div(to.C / 8, 32) * 32;
+        DAD3D_REQUIRE(cthreads <= 1024, "concat: too many channels");
+        fusion_concat_kernel<<<dim3(static_cast<unsigned>(to.H * to.W), static_cast<unsigned>(to.N)), cthreads, 0, stream>>>(
             view(s.in), T(s.in).C, reinterpret_cast<const float*>(th.ptr), th.H, th.W, th.C, kHeat, kHeatCat, view(s.in3),
             T(s.in3).C, to.N, to.H, to.W, reinterpret_cast<uint16_t*>(to.ptr), to.plane_elems(), to.planes, enc->fp16);
         count_launch();

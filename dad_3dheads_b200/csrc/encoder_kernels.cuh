@@ -476,17 +476,19 @@ struct FuseSrc {
   int H, W;       // source extents
   float w;
 };
-__global__ void bifpn_fuse_kernel(FuseSrc s0, FuseSrc s1, FuseSrc s2, int nsrc, int B, int H, int W, int C,
-                                  uint16_t* __restrict__ out, long long out_plane, int planes, int fp16) {
-  const int cgs = C / 8;
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long total = static_cast<long long>(B) * H * W * cgs;
-  if (i >= total) return;
-  const int cg = static_cast<int>(i % cgs);
-  const long long pix = i / cgs;
-  const int x = static_cast<int>(pix % W);
-  const int y = static_cast<int>((pix / W) % H);
-  const long long b = pix / (static_cast<long long>(W) * H);
+// grid = (ceil(W * C/8 / 256), H, B): the row and the image come from the block index, so the only division per thread is a
+// 32-bit one (the 64-bit div/mod chain of a flat index was most of this kernel's time)
+__global__ void __launch_bounds__(256)
+bifpn_fuse_kernel(FuseSrc s0, FuseSrc s1, FuseSrc s2, int nsrc, int B, int H, int W, int C,
+                  uint16_t* __restrict__ out, long long out_plane, int planes, int fp16) {
+  const unsigned cgs = static_cast<unsigned>(C) >> 3;
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= static_cast<unsigned>(W) * cgs) return;
+  const int x = static_cast<int>(t / cgs);
+  const int cg = static_cast<int>(t - static_cast<unsigned>(x) * cgs);
+  const int y = blockIdx.y;
+  const long long b = blockIdx.z;
+  const long long pix = (b * H + y) * W + x;
   float acc[8], t0[8], t1[8], t2[8];
   act_load8(s0.v, pix * C + cg * 8, t0);
   {
@@ -512,21 +514,20 @@ __global__ void bifpn_fuse_kernel(FuseSrc s0, FuseSrc s1, FuseSrc s2, int nsrc, 
 __global__ void fusion_concat_kernel(ActView x, int Cx, const float* __restrict__ heat, int Hh, int Wh, int ldh,
                                      int n_heat, int Ch_pad, ActView p5, int Cp, int B, int H, int W,
                                      uint16_t* __restrict__ out, long long out_plane, int planes, int fp16) {
+  // grid = (pixels of one image, B), block = the Ct/8 channel groups of a pixel (rounded up to a warp multiple)
   const int Ct = Cx + Ch_pad + Cp;
-  const int cgs = Ct / 8;
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long total = static_cast<long long>(B) * H * W * cgs;
-  if (i >= total) return;
-  const int cg = static_cast<int>(i % cgs);
-  const long long pix = i / cgs;
+  const int cg = threadIdx.x;
+  if (cg >= Ct / 8) return;
+  const long long b = blockIdx.y;
+  const int pin = blockIdx.x;                      // pixel inside the image
+  const long long pix = b * (static_cast<long long>(H) * W) + pin;
   const int c = cg * 8;
   float v[8];
   if (c < Cx) {
     act_load8(x, pix * Cx + c, v);
   } else if (c < Cx + Ch_pad) {
-    const int px = static_cast<int>(pix % W);
-    const int py = static_cast<int>((pix / W) % H);
-    const long long b = pix / (static_cast<long long>(W) * H);
+    const int py = pin / W;
+    const int px = pin - py * W;
     // align_corners=True: src = dst * (in - 1) / (out - 1)
     const float fy = (H > 1) ? py * (static_cast<float>(Hh - 1) / static_cast<float>(H - 1)) : 0.f;
     const float fx = (W > 1) ? px * (static_cast<float>(Wh - 1) / static_cast<float>(W - 1)) : 0.f;
