@@ -900,8 +900,8 @@ int dad3d_encoder_forward(dad3d_encoder* enc, const float* images_d, int32_t B, 
       }
       case kStemS2d: {
         const TensorInfo& to = T(s.out);
-        const long long total = static_cast<long long>(B) * to.H * to.W;
-        stem_s2d_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+        stem_s2d_kernel<<<dim3(static_cast<unsigned>(ceil_div(to.W, 128)), static_cast<unsigned>(to.H), static_cast<unsigned>(B)),
+                          128, 0, stream>>>(
             images_d, B, kImg, kImg, reinterpret_cast<uint16_t*>(to.ptr), to.plane_elems(), to.planes, enc->fp16);
         count_launch();
         break;
@@ -909,10 +909,10 @@ int dad3d_encoder_forward(dad3d_encoder* enc, const float* images_d, int32_t B, 
       case kStemPool: {
         const TensorInfo& ti = T(s.in);
         const TensorInfo& to = T(s.out);
-        const long long total = static_cast<long long>(B) * to.H * to.W * 8;
         ActView pieces{nullptr, 0, 0, 0, enc->fp16};
         if (!ti.f32) pieces = view(s.in);
-        stem_pool_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+        stem_pool_kernel<<<dim3(static_cast<unsigned>(ceil_div(to.W * 8, 256)), static_cast<unsigned>(to.H),
+                                static_cast<unsigned>(B)), 256, 0, stream>>>(
             reinterpret_cast<const float*>(ti.ptr), pieces, B, ti.H, ti.W, reinterpret_cast<uint16_t*>(to.ptr),
             to.plane_elems(), to.planes, enc->fp16);
         count_launch();

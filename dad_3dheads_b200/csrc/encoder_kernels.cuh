@@ -401,13 +401,13 @@ constexpr int kS2dPadL = 2;
 constexpr int kS2dPadW = 4;      // total horizontal padding (row pitch W/2 + 4)
 __global__ void stem_s2d_kernel(const float* __restrict__ img, int B, int H, int W, uint16_t* __restrict__ out,
                                 long long out_plane, int planes, int fp16) {
+  // grid = (ceil(Wp / 128), Hs, B)
   const int Hs = H / 2, Ws = W / 2, Wp = Ws + kS2dPadW;
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long total = static_cast<long long>(B) * Hs * Wp;
-  if (i >= total) return;
-  const int xp = static_cast<int>(i % Wp);
-  const int y = static_cast<int>((i / Wp) % Hs);
-  const long long b = i / (static_cast<long long>(Wp) * Hs);
+  const int xp = blockIdx.x * blockDim.x + threadIdx.x;
+  if (xp >= Wp) return;
+  const int y = blockIdx.y;
+  const long long b = blockIdx.z;
+  const long long i = (b * Hs + y) * Wp + xp;
   float v[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) v[j] = 0.f;
@@ -433,15 +433,15 @@ __global__ void stem_s2d_kernel(const float* __restrict__ img, int B, int H, int
 // `in` is fp32 NHWC (SIMT stem) when in_pieces.base == nullptr, otherwise the piece tensor written by the tensor-core stem.
 __global__ void stem_pool_kernel(const float* __restrict__ in, ActView in_pieces, int B, int Hi, int Wi,
                                  uint16_t* __restrict__ out, long long out_plane, int planes, int fp16) {
+  // grid = (ceil(Wo * 8 / 256), Ho, B)
   const int Ho = Hi / 2, Wo = Wi / 2;
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long total = static_cast<long long>(B) * Ho * Wo * 8;
-  if (i >= total) return;
-  const int cg = static_cast<int>(i & 7);
-  const long long pix = i >> 3;
-  const int ox = static_cast<int>(pix % Wo);
-  const int oy = static_cast<int>((pix / Wo) % Ho);
-  const long long b = pix / (static_cast<long long>(Wo) * Ho);
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= Wo * 8) return;
+  const int cg = t & 7;
+  const int ox = t >> 3;
+  const int oy = blockIdx.y;
+  const long long b = blockIdx.z;
+  const long long pix = (b * Ho + oy) * Wo + ox;
   float m[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
