@@ -17,12 +17,18 @@
 // products go to accumulator 0 and all the small correction products to accumulator 1; the epilogue adds the two in
 // fp32 with round-to-nearest.  That cuts the number of truncating steps on the large accumulator by n_mma (6x / 3x).
 //
-// Roles (320 threads): warp 0 = TMEM allocator + TMA producer (one lane), warp 1 = barrier init + MMA issuer (one lane),
+// Roles (320 threads): warp 0 = TMEM allocator + TMA producer, warp 1 = barrier init + MMA issuer -- both walk their schedule
+// with all 32 lanes converged and one elect.sync lane issues the TMA / tcgen05 instructions (operands stay in uniform
+// registers; gating the warps on lane == 0 instead costs an ELECT..BRA.U.ANY loop per instruction, ~140 cycles per MMA);
 // warps 2..9 = epilogue: warp w owns TMEM lanes 32*(w%4).. (accumulator rows) and column group (w-2)/4 (half of the
 // tile's columns), i.e. two epilogue warps per SM sub-partition so their dependent-issue stalls overlap.
 // Pipelines: smem ring (full/empty mbarriers) between TMA and MMA; two TMEM accumulator buffers (tmem_full/tmem_empty)
 // between MMA and epilogue, so the epilogue of tile i overlaps the main loop of tile i+1.  Each epilogue warp owns a
-// 4 KiB shared-memory staging tile from which it issues TMA stores of its 32 rows x (32|64) channels.
+// 4 KiB shared-memory staging area (two 2 KiB store tiles used alternately) from which it issues TMA stores of its
+// 32 rows x 32 channels.
+// Variants selected per launch in GemmGeom: halo (3x3 stride-1 convolutions: one halo patch per channel block feeds all nine
+// taps through shifted descriptors; separate weights ring), res_kb / res_kind (residual or second source on the K axis),
+// cl_m x cl_n multicast clusters, pair (cta_group::2, template parameter kPair).
 #pragma once
 #include "ptx.cuh"
 
