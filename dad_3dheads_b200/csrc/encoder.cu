@@ -911,8 +911,9 @@ int dad3d_encoder_forward(dad3d_encoder* enc, const float* images_d, int32_t B, 
         const TensorInfo& to = T(s.out);
         ActView pieces{nullptr, 0, 0, 0, enc->fp16};
         if (!ti.f32) pieces = view(s.in);
-        stem_pool_kernel<<<dim3(static_cast<unsigned>(ceil_div(to.W * 8, 256)), static_cast<unsigned>(to.H),
-                                static_cast<unsigned>(B)), 256, 0, stream>>>(
+        const long long total = static_cast<long long>(B) * to.H * to.W * 8;
+        DAD3D_REQUIRE(total < (1ll << 31), "pool: batch too large for 32-bit indexing");
+        stem_pool_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
             reinterpret_cast<const float*>(ti.ptr), pieces, B, ti.H, ti.W, reinterpret_cast<uint16_t*>(to.ptr),
             to.plane_elems(), to.planes, enc->fp16);
         count_launch();

@@ -433,15 +433,17 @@ __global__ void stem_s2d_kernel(const float* __restrict__ img, int B, int H, int
 // `in` is fp32 NHWC (SIMT stem) when in_pieces.base == nullptr, otherwise the piece tensor written by the tensor-core stem.
 __global__ void stem_pool_kernel(const float* __restrict__ in, ActView in_pieces, int B, int Hi, int Wi,
                                  uint16_t* __restrict__ out, long long out_plane, int planes, int fp16) {
-  // grid = (ceil(Wo * 8 / 256), Ho, B)
+  // flat index over (image, row, column, channel group); 32-bit div/mod (B * Ho * Wo * 8 < 2^31 is checked by the host)
   const int Ho = Hi / 2, Wo = Wi / 2;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= Wo * 8) return;
-  const int cg = t & 7;
-  const int ox = t >> 3;
-  const int oy = blockIdx.y;
-  const long long b = blockIdx.z;
-  const long long pix = (b * Ho + oy) * Wo + ox;
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= static_cast<unsigned>(B) * Ho * Wo * 8u) return;
+  const int cg = static_cast<int>(i & 7u);
+  const unsigned upix = i >> 3;
+  const int ox = static_cast<int>(upix % static_cast<unsigned>(Wo));
+  const unsigned t2 = upix / static_cast<unsigned>(Wo);
+  const int oy = static_cast<int>(t2 % static_cast<unsigned>(Ho));
+  const long long b = t2 / static_cast<unsigned>(Ho);
+  const long long pix = upix;
   float m[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
