@@ -87,6 +87,8 @@ struct Step {
   const ConvW* w = nullptr;
   int stride = 1, pad = 0, relu = 0, res_mode = 0, res_stride = 1;
   int up2 = 0;                  // output stored 2x nearest-up-sampled ([N, 2Ho, 2Wo, C])
+  int parity = 0;               // 1 + 2a + b: 1x1 conv over the input pixels (2i + a, 2j + b) only, output stored to the same
+                                // pixels of the full-resolution tensor; the residual (res) lives on the half-resolution grid
   int stem = 0;                 // the stem as a GEMM: input = space-to-depth image, A map = overlapping 4-pixel windows
   GemmMaps maps;
   GemmGeom geom;
@@ -270,7 +272,8 @@ int build_graph(Builder& b) {
   const int c2 = c_out[0], c3 = c_out[1], c4 = c_out[2];
   // ---- BiFPN laterals (bifpn.py:137-145, 152-161)
   int feat[5];
-  feat[0] = b.conv("lat3", c2, 1, 0, false);
+  // P3's lateral conv is normally composed into b0_p3td on the host (its only consumer); a "lat3" record keeps it separate
+  feat[0] = b.W("lat3") ? b.conv("lat3", c2, 1, 0, false) : c2;
   feat[1] = b.conv("lat4", c3, 1, 0, false);
   feat[2] = b.conv("lat5", c4, 1, 0, false);
   feat[3] = b.conv("lat6", c4, 2, 1, false);
@@ -297,9 +300,30 @@ int build_graph(Builder& b) {
     // top-down nodes (bifpn.py:111-114): node(w0*a + w1*up(b)) = relu(W0 a + up(W1 b) + shift); the fusion scalars are
     // folded into the two weight sets on the host.  The low-resolution product is stored nearest-up-sampled (every pixel
     // to its 2x2 block) and enters the node's GEMM through identity columns on the K axis, like a ResUnit residual.
+    // Large maps (>= 32 rows): the up-sampled branch is never materialised -- the node runs as four launches, one per pixel
+    // parity (a, b): a stride-2 view of the input starting at (a, b), the half-resolution product as the K-axis residual,
+    // and a store to the pixels (2i + a, 2j + b).  Small maps keep the single launch with the 4x store (fewer launches).
     auto td_node = [&](const std::string& name, int a, int lower) {
-      const int u = b.conv(name + "_u", lower, 1, 0, false, -1, 0, false, true, nullptr, 1, /*up2=*/true);
-      return b.conv(name, a, 1, 0, true, u, 1);
+      const TensorInfo ta = plan->tensors[a];
+      if (ta.H < 32) {
+        const int u = b.conv(name + "_u", lower, 1, 0, false, -1, 0, false, true, nullptr, 1, /*up2=*/true);
+        return b.conv(name, a, 1, 0, true, u, 1);
+      }
+      const int u = b.conv(name + "_u", lower, 1, 0, false);
+      const ConvW* w = b.W(name);
+      const int out = b.tensor(ta.N, ta.H, ta.W, w->cout_pad);
+      plan->tensors[out].name = name;
+      for (int ab = 0; ab < 4; ++ab) {
+        Step s;
+        std::memset(&s.maps, 0, sizeof(s.maps));
+        s.kind = kConv;
+        s.in = a; s.w = w; s.stride = 2; s.pad = 0; s.relu = 1;
+        s.res = u; s.res_mode = 1;
+        s.out = out;
+        s.parity = 1 + ab;
+        b.push(s);
+      }
+      return out;
     };
     const int p6td = td_node(p + "p6td", p6x, p7td);
     const int p5td = td_node(p + "p5td", p5x, p6td);
@@ -427,8 +451,8 @@ int make_plan(dad3d_encoder* enc, int B, void* ws, size_t ws_bytes, bool layout_
                 " channels, weights expect " + std::to_string(w->cin_pad));
       return DAD3D_ERR_INVALID;
     }
-    const int Ho = s.stem ? ti.H : (ti.H + 2 * s.pad - w->R) / s.stride + 1;
-    const int Wo = s.stem ? ti.W - kS2dPadW : (ti.W + 2 * s.pad - w->S) / s.stride + 1;
+    const int Ho = s.stem ? ti.H : s.parity ? ti.H / 2 : (ti.H + 2 * s.pad - w->R) / s.stride + 1;
+    const int Wo = s.stem ? ti.W - kS2dPadW : s.parity ? ti.W / 2 : (ti.W + 2 * s.pad - w->S) / s.stride + 1;
     GemmGeom& g = s.geom;
     std::memset(&g, 0, sizeof(g));
     pick_tile(Wo, Ho, &g.tw, &g.th, &g.tn);
@@ -451,6 +475,7 @@ int make_plan(dad3d_encoder* enc, int B, void* ws, size_t ws_bytes, bool layout_
     g.R = w->R; g.S = w->S; g.pad_h = s.pad; g.pad_w = s.pad;
     g.cin_blocks = ti.C / kBlockK;                    // main source; a second source adds res_kb blocks below
     if (s.stem) { g.cin_blocks = 1; g.pad_h = 2; g.pad_w = 0; }   // 4 vertical taps x one 64-element window
+    if (s.parity) { g.pad_h = -((s.parity - 1) >> 1); g.pad_w = -((s.parity - 1) & 1); }   // input pixel (2i + a, 2j + b)
     g.cl_m = 1; g.cl_n = 1;
     const bool res_in_k = s.res >= 0 && s.res_mode == 1 && w->has_identity;
     // few row tiles (small maps / small batch): halve the tile width so that twice as many CTAs share the work
@@ -530,6 +555,7 @@ int make_plan(dad3d_encoder* enc, int B, void* ws, size_t ws_bytes, bool layout_
     ep.res_mode = (res_in_k || src2) ? 0 : s.res_mode;
     ep.res = view(s.res);
     ep.up2 = s.up2;
+    ep.parity = s.parity;
     if (s.res >= 0 && !src2 && plan->tensors[s.res].C != w->cout_pad) {
       set_error("layer " + w->name + ": residual channel mismatch");
       return DAD3D_ERR_INVALID;
@@ -551,7 +577,7 @@ int make_plan(dad3d_encoder* enc, int B, void* ws, size_t ws_bytes, bool layout_
       const int bn = 32 / (bw * bh);
       for (int p = 0; p < to.planes; ++p) {
         uint16_t* basep = reinterpret_cast<uint16_t*>(to.ptr) + static_cast<size_t>(p) * to.plane_elems();
-        if (s.up2) {
+        if (s.up2 || s.parity) {
           // [N, 2Ho, 2Wo, C] seen as (C, b, j, a, n*Ho + i): pixel (2i + a, 2j + b); a box with b = a = 1 addresses the
           // sub-grid of one parity, so the same staging tile is stored four times
           const uint64_t C2 = static_cast<uint64_t>(to.C) * 2;
@@ -823,7 +849,7 @@ int dad3d_encoder_create(dad3d_encoder** out, const dad3d_conv_weights* layers, 
   }
   // every layer the graph needs must be present
   {
-    std::vector<std::string> need = {"lat3", "lat4", "lat5", "lat6", "lat7", "heat", "fusion", "mlp1", "mlp2"};
+    std::vector<std::string> need = {"lat4", "lat5", "lat6", "lat7", "heat", "fusion", "mlp1", "mlp2"};
     for (int si = 0; si < 4; ++si)
       for (int ui = 0; ui < kStageUnits[si]; ++ui) {
         const std::string p = "s" + std::to_string(si + 1) + "u" + std::to_string(ui + 1);

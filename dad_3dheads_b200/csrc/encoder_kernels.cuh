@@ -118,6 +118,8 @@ struct EpiConvParams {
     ActView res;              // as the output.  (ResUnit / BiFPN residual adds normally ride the K axis instead.)
     int up2;                  // store every output pixel to the 2x2 block it covers in a [N, 2H, 2W, C] tensor (nearest
                               // up-sampling fused into the store: maps.c are 5-D parity views, see make_plan)
+    int parity;               // 1 + 2a + b: this launch computes the output pixels (2i + a, 2j + b) of a [N, 2H, 2W, C] tensor
+                              // (tile grid = the half-resolution grid) and stores them through the same 5-D view
     uint16_t* out;            // piece planes [planes][pix][ld_out]; may be null when only out_f32 is wanted
     long long out_plane;
     int out_planes;
@@ -287,6 +289,9 @@ struct EpiConvT {
           const int row0 = c.bn0 * c.g->Ho + c.bh0;   // merged (image, row) coordinate of the 5-D parity view
 #pragma unroll
           for (int ab = 0; ab < 4; ++ab) ptx::tma_store_5d(&c.maps->c[p], tile, col, ab & 1, c.bw0, ab >> 1, row0);
+        } else if (ep.parity) {
+          ptx::tma_store_5d(&c.maps->c[p], tile, col, (ep.parity - 1) & 1, c.bw0, (ep.parity - 1) >> 1,
+                            c.bn0 * c.g->Ho + c.bh0);
         } else {
           ptx::tma_store_4d(&c.maps->c[p], tile, col, c.bw0, c.bh0, c.bn0);
         }

@@ -69,7 +69,11 @@ def fold_state_dict(sd: Dict[str, Tensor]) -> Tuple[List[Tuple[str, np.ndarray, 
                 add(n + "c3", torch.cat([w3, wi], dim=1), sh3 + shi)
             else:
                 conv_bn(n + "c3", p + ".body.conv3")
-    for lvl in (3, 4, 5, 6):
+    # lateral convs (plain 1x1 + bias, no activation).  P3's lateral feeds exactly one consumer -- the first block's p3_td
+    # node, also a 1x1 -- so the two are composed on the host (fp64) and the 64x64x256 lateral map is never materialised
+    lat3_w = sd["bifpn.p3.weight"].double()[:, :, 0, 0]
+    lat3_b = sd["bifpn.p3.bias"].double()
+    for lvl in (4, 5, 6):
         add(f"lat{lvl}", sd[f"bifpn.p{lvl}.weight"].double(), sd[f"bifpn.p{lvl}.bias"].double())
     s, sh = _bn_scale_shift(sd, "bifpn.p7.bn", BN_EPS_BIFPN)       # BiFPNConvBlock: conv(bias) -> BN -> ReLU
     add("lat7", sd["bifpn.p7.conv.weight"].double() * s[:, None, None, None],
@@ -93,7 +97,12 @@ def fold_state_dict(sd: Dict[str, Tensor]) -> Tuple[List[Tuple[str, np.ndarray, 
                 # top-down node: node(w0*a + w1*up(b)) = relu(W(w0 a) + up(W(w1 b)) + shift) because a 1x1 conv commutes with
                 # nearest up-sampling -> two GEMMs (the second at the lower resolution), no separate weighted-sum pass
                 j = td_col[node]
-                add(name, wfull * fw["w1"][0, j], sh)
+                w_main = wfull * fw["w1"][0, j]
+                if li == 0 and node == "p3_td":                  # W0' (Wl c2 + bl) = (W0' Wl) c2 + W0' bl
+                    w2d = w_main[:, :, 0, 0]
+                    add(name, (w2d @ lat3_w)[:, :, None, None], sh + w2d @ lat3_b)
+                else:
+                    add(name, w_main, sh)
                 add(name + "_u", wfull * fw["w1"][1, j], torch.zeros_like(sh))
             else:
                 add(name, wfull, sh)

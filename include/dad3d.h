@@ -102,7 +102,8 @@ DAD3D_API int dad3d_gather_landmarks_bary(const float* src_d, int32_t B, int32_t
  *   "stem" (7x7 3->64)                       encoder.model.init_block.conv
  *   "s{1..4}u{k}c{1,2,3}"                    encoder.model.stage{i}.unit{k}.body.conv{1,2,3}; the first unit's c3 carries
  *                                            the projection shortcut K-concatenated: [W3 | W_identity_conv], bias b3 + bid
- *   "lat3".."lat7"                           bifpn.p3 .. bifpn.p7
+ *   "lat4".."lat7" (+ optional "lat3")      bifpn.p4 .. bifpn.p7; bifpn.p3 is normally composed into "b0_p3td" (its only
+ *                                            consumer: (W_node W_p3) c2 + W_node b_p3), a "lat3" record keeps it separate
  *   "b{0,1}_{p4out,p5out,p6out,p7out}"       bifpn.bifpn.{0,1}.<node> (depthwise scale, pointwise, BN folded)
  *   "b{0,1}_{p6td,p5td,p4td,p3td}" and "..._u"   top-down nodes split in two: W*(w0 a) at the node's resolution and
  *                                            W*(w1 b) at the lower one (fusion scalars folded in; the second has no bias)

@@ -50,7 +50,8 @@ def run_folded(x: torch.Tensor, layers, fusion_w: np.ndarray, dtype=torch.float6
     c2 = stage(0, y)
     c3 = stage(1, c2)
     c4 = stage(2, c3)
-    feat = [conv("lat3", c2), conv("lat4", c3), conv("lat5", c4), conv("lat6", c4, 2, 1)]
+    # P3's lateral is composed into b0_p3td by fold_state_dict (no "lat3" layer): the first block's P3 input is c2 itself
+    feat = [conv("lat3", c2) if "lat3" in L else c2, conv("lat4", c3), conv("lat5", c4), conv("lat6", c4, 2, 1)]
     feat.append(conv("lat7", feat[3], 2, 1, True))
     near = lambda t, ref: F.interpolate(t, size=ref.shape[2:])
     for li in range(2):
@@ -62,8 +63,10 @@ def run_folded(x: torch.Tensor, layers, fusion_w: np.ndarray, dtype=torch.float6
         # top-down nodes: fusion weights are folded into the two weight sets; the low-res product is stored nearest-up-sampled
         # (that is the activation the engine keeps under the "_u" name) and added
         def up(name, low, ref):
-            acts[name] = near(conv(name, low), ref)
-            return acts[name]
+            u = near(conv(name, low), ref)          # conv() recorded the half-resolution product under `name`
+            if ref.shape[2] < 32:                   # small maps: the engine stores it up-sampled (4x store); large maps keep
+                acts[name] = u                      # it at half resolution and run the node once per pixel parity
+            return u
         p6td = conv(p + "p6td", p6x, relu=True, res=up(p + "p6td_u", p7td, p6x))
         p5td = conv(p + "p5td", p5x, relu=True, res=up(p + "p5td_u", p6td, p5x))
         p4td = conv(p + "p4td", p4x, relu=True, res=up(p + "p4td_u", p5td, p4x))

@@ -21,7 +21,8 @@ def test_folded_graph_matches_oracle_fp64():
     sd = synthetic_state_dict(1)
     layers, fw = fold_state_dict(sd)
     names = [n for n, _, _ in layers]
-    assert len(names) == len(set(names)) == 53 - 4 + 5 + 16 + 8 + 4    # 4 shortcuts fused into c3, + 8 low-res halves of the top-down nodes
+    # 4 shortcuts fused into c3, P3 lateral composed into b0_p3td, + 8 low-res halves of the top-down nodes
+    assert len(names) == len(set(names)) == 53 - 4 + 4 + 16 + 8 + 4
     x = torch.randn(1, 3, 256, 256, generator=torch.Generator().manual_seed(3))
     with torch.no_grad():
         ref = flame_regression_forward(x.double(), {k: v.double() for k, v in sd.items()})
