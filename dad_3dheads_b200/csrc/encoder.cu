@@ -126,6 +126,7 @@ struct dad3d_encoder {
   bool stem_simt = false;          // env DAD3D_STEM_SIMT=1: run the stem on the fp32 CUDA-core kernel instead of the tile engine
   bool use_halo = true;            // halo-reuse tiles for the 3x3 stride-1 layers (env DAD3D_HALO=0 selects the per-tap path)
   int halo_cluster = 1;            // env DAD3D_HALO_CLUSTER=2: halo layers run as clusters of 2 row tiles that multicast the weights
+  bool td_parity = false;          // env DAD3D_TD_PARITY=1: large top-down nodes as four parity launches
   bool use_pair = false;           // env DAD3D_PAIR=1: cta_group::2 CTA pairs for the large 128-wide layers
   bool use_pdl = false;            // programmatic dependent launch for the tile-engine kernels (env DAD3D_PDL=1 enables;
                                    // measured neutral on B200 at batch 64: 6689 vs 6764 heads/s, so off by default)
@@ -300,12 +301,13 @@ int build_graph(Builder& b) {
     // top-down nodes (bifpn.py:111-114): node(w0*a + w1*up(b)) = relu(W0 a + up(W1 b) + shift); the fusion scalars are
     // folded into the two weight sets on the host.  The low-resolution product is stored nearest-up-sampled (every pixel
     // to its 2x2 block) and enters the node's GEMM through identity columns on the K axis, like a ResUnit residual.
-    // Large maps (>= 32 rows): the up-sampled branch is never materialised -- the node runs as four launches, one per pixel
-    // parity (a, b): a stride-2 view of the input starting at (a, b), the half-resolution product as the K-axis residual,
-    // and a store to the pixels (2i + a, 2j + b).  Small maps keep the single launch with the 4x store (fewer launches).
+    // DAD3D_TD_PARITY=1, maps of >= 32 rows: the up-sampled branch is never materialised -- the node runs as four launches,
+    // one per pixel parity (a, b): a stride-2 view of the input starting at (a, b), the half-resolution product as the
+    // K-axis residual, and a store to the pixels (2i + a, 2j + b).  Measured slower than the default (one launch over the
+    // full map with the 4x-stored branch as residual: P3 node 222 -> 231 us, P4 73 -> 103 us), so it is opt-in.
     auto td_node = [&](const std::string& name, int a, int lower) {
       const TensorInfo ta = plan->tensors[a];
-      if (ta.H < 32) {
+      if (!b.enc->td_parity || ta.H < 32) {
         const int u = b.conv(name + "_u", lower, 1, 0, false, -1, 0, false, true, nullptr, 1, /*up2=*/true);
         return b.conv(name, a, 1, 0, true, u, 1);
       }
@@ -725,6 +727,8 @@ int dad3d_encoder_create(dad3d_encoder** out, const dad3d_conv_weights* layers, 
     enc->use_halo = !(e4 && e4[0] == '0');
     const char* e5 = std::getenv("DAD3D_HALO_CLUSTER");
     enc->halo_cluster = (e5 && e5[0] == '2') ? 2 : 1;
+    const char* e6 = std::getenv("DAD3D_TD_PARITY");
+    enc->td_parity = (e6 && e6[0] == '1');
     const char* e3 = std::getenv("DAD3D_PAIR");
     enc->use_pair = (e3 && e3[0] == '1');
     const char* e2 = std::getenv("DAD3D_STEM_SIMT");

@@ -2,6 +2,7 @@
 csrc/encoder.cu.  Two uses: (1) on CPU it pins the folding (BN fold, K layouts, block-diagonal heads, fusion scalars)
 against the oracle; (2) on the GPU box it gives per-layer expected activations, by the library's layer names, so a
 mismatch is localised to one kernel."""
+import os
 from typing import Dict
 
 import numpy as np
@@ -64,9 +65,9 @@ def run_folded(x: torch.Tensor, layers, fusion_w: np.ndarray, dtype=torch.float6
         # (that is the activation the engine keeps under the "_u" name) and added
         def up(name, low, ref):
             u = near(conv(name, low), ref)          # conv() recorded the half-resolution product under `name`
-            if ref.shape[2] < 32:                   # small maps: the engine stores it up-sampled (4x store); large maps keep
-                acts[name] = u                      # it at half resolution and run the node once per pixel parity
-            return u
+            if ref.shape[2] < 32 or os.environ.get("DAD3D_TD_PARITY") != "1":
+                acts[name] = u                      # the engine stores it up-sampled (4x store); in the opt-in parity mode
+            return u                                # large maps keep it at half resolution
         p6td = conv(p + "p6td", p6x, relu=True, res=up(p + "p6td_u", p7td, p6x))
         p5td = conv(p + "p5td", p5x, relu=True, res=up(p + "p5td_u", p6td, p5x))
         p4td = conv(p + "p4td", p4x, relu=True, res=up(p + "p4td_u", p5td, p4x))

@@ -157,6 +157,29 @@ def test_halo_and_per_tap_paths_match_oracle(sd, ref5, cuda_device, monkeypatch,
     assert all(e < tol for e in errs.values()), errs
 
 
+def test_td_parity_launches_match(sd, cuda_device, monkeypatch):
+    """DAD3D_TD_PARITY=1: P3 / P4 top-down nodes as four launches, one per pixel parity (strided A view, half-resolution
+    residual, parity store); every activation against the CPU executor of the folded graph."""
+    from dad_3dheads_b200.encoder import Dad3dEncoder, fold_state_dict
+    from tests.folded_ref import run_folded
+    monkeypatch.setenv("DAD3D_TD_PARITY", "1")
+    x = torch.randn(2, 3, 256, 256, generator=torch.Generator().manual_seed(11))
+    layers, fw = fold_state_dict(sd)
+    with torch.no_grad():
+        ref = run_folded(x, layers, fw)
+    enc = Dad3dEncoder(sd, cuda_device, precision="fp16x2")
+    enc.set_debug(True)
+    enc.forward_raw(x.to(cuda_device))
+    bad = {}
+    for name in [n for n, _, _ in layers if n.startswith("b0_") or n.startswith("b1_")]:
+        a = enc.read_activation(name)
+        r = ref[name]
+        e = _rel(a[..., : r.shape[1]].permute(0, 3, 1, 2), r)
+        if e > 5e-5:
+            bad[name] = e
+    assert not bad, bad
+
+
 def test_encoder_golden_fixture(sd, cuda_device):
     """tests/golden/encoder_golden.npz (tools/make_golden.py: fp64 oracle, weight seed 0, image seed 777)."""
     import os
