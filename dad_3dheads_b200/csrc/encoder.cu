@@ -126,6 +126,7 @@ struct dad3d_encoder {
   bool stem_simt = false;          // env DAD3D_STEM_SIMT=1: run the stem on the fp32 CUDA-core kernel instead of the tile engine
   bool use_halo = true;            // halo-reuse tiles for the 3x3 stride-1 layers (env DAD3D_HALO=0 selects the per-tap path)
   int halo_cluster = 1;            // env DAD3D_HALO_CLUSTER=2: halo layers run as clusters of 2 row tiles that multicast the weights
+  bool kernels_configured = false, stem_configured = false;   // cudaFuncSetAttribute done on this handle's device
   bool td_parity = false;          // env DAD3D_TD_PARITY=1: large top-down nodes as four parity launches
   bool use_pair = false;           // env DAD3D_PAIR=1: cta_group::2 CTA pairs for the large 128-wide layers
   bool use_pdl = false;            // programmatic dependent launch for the tile-engine kernels (env DAD3D_PDL=1 enables;
@@ -620,13 +621,12 @@ double conv_useful_flops(const Step& s) {
 }
 
 int launch_conv(dad3d_encoder* enc, const Step& s, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
+  if (!enc->kernels_configured) {                  // function attributes are per device: remembered per handle
     DAD3D_CUDA_OK(cudaFuncSetAttribute(tile_gemm_kernel<EpiConv>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemLimit));
     DAD3D_CUDA_OK(cudaFuncSetAttribute(tile_gemm_kernel<EpiConvH>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemLimit));
     DAD3D_CUDA_OK(cudaFuncSetAttribute(tile_gemm_kernel<EpiConvH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemLimit));
     DAD3D_CUDA_OK(cudaFuncSetAttribute(tile_gemm_kernel<EpiConv, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemLimit));
-    configured = true;
+    enc->kernels_configured = true;
   }
   const GemmGeom& g = s.geom;
   const int m_tiles_total = g.tiles_w * g.tiles_h * g.tiles_n;
@@ -918,10 +918,9 @@ int dad3d_encoder_forward(dad3d_encoder* enc, const float* images_d, int32_t B, 
       case kStemConv: {
         const TensorInfo& to = T(s.out_f32);
         dim3 grid(ceil_div(to.W, kStemTile), ceil_div(to.H, kStemTile), B);
-        static bool stem_configured = false;
-        if (!stem_configured) {
+        if (!enc->stem_configured) {
           DAD3D_CUDA_OK(cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemSmemBytes));
-          stem_configured = true;
+          enc->stem_configured = true;
         }
         stem_conv_kernel<<<grid, 256, kStemSmemBytes, stream>>>(images_d, enc->d_stem_w, enc->d_stem_b, kImg, kImg,
                                                    reinterpret_cast<float*>(to.ptr));

@@ -489,6 +489,7 @@ using namespace dad3d;
 
 struct dad3d_flame {
   int device = 0;
+  int smem_configured[2] = {0, 0};           // per handle (= per device): max dynamic smem set for <EpiLbs> / <EpiBlend>
   int nv = 0, n3 = 0, npad = 0;
   int num_sms = 0;
   FlameLayoutDev layout{};
@@ -509,12 +510,12 @@ namespace {
 
 template <class Epi>
 int launch_tile_gemm(const GemmMaps& maps, const GemmGeom& g, const typename Epi::Params& ep, int num_sms,
-                     cudaStream_t stream) {
-  static int configured_smem = 0;
+                     cudaStream_t stream, int* configured) {
+  // function attributes are per device: remembered in the handle, not in a process-wide static
   const int smem = gemm_smem_bytes(g, Epi::kExtraSmemBytes);
-  if (smem > configured_smem) {
+  if (!*configured) {
     DAD3D_CUDA_OK(cudaFuncSetAttribute(tile_gemm_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemLimit));
-    configured_smem = kGemmSmemLimit;
+    *configured = 1;
   }
   const int m_tiles = g.tiles_w * g.tiles_h * g.tiles_n;
   const int csize = g.cl_m * g.cl_n;
@@ -827,13 +828,13 @@ int dad3d_flame_decode(dad3d_flame* h, const float* params_d, int32_t B, int32_t
         g.sched = g.tiles_w >= h->num_sms ? 1 : 0;          // enough row tiles to give every SM its own
         g.stages = gemm_max_stages(g, EpiLbs::kExtraSmemBytes);
         EpiLbs::Params ep{xf, h->d_w2, h->nv, v3, pj, pc, image_size};
-        int rc = launch_tile_gemm<EpiLbs>(maps, g, ep, h->num_sms, stream);
+        int rc = launch_tile_gemm<EpiLbs>(maps, g, ep, h->num_sms, stream, &h->smem_configured[0]);
         if (rc != DAD3D_OK) return rc;
       } else {
         g.sched = 0;
         g.stages = gemm_max_stages(g);
         EpiBlend::Params ep{vposed, h->npad};
-        int rc = launch_tile_gemm<EpiBlend>(maps, g, ep, h->num_sms, stream);
+        int rc = launch_tile_gemm<EpiBlend>(maps, g, ep, h->num_sms, stream, &h->smem_configured[1]);
         if (rc != DAD3D_OK) return rc;
       }
     }
