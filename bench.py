@@ -431,7 +431,22 @@ def cpu_baseline(sd, static, parity_with=None):
         po.predict_batch(x)
         reps += 1
     dt = time.perf_counter() - t0
+    # per-stage split and the single-image latency of BASELINE configs[0] (one letter-boxed 256x256 frame through the
+    # reference's __call__ path), a few passes each
+    def clock(fn, n):
+        fn()
+        t = time.perf_counter()
+        for _ in range(n):
+            fn()
+        return (time.perf_counter() - t) / n
+    t_enc = clock(lambda: po.encode(x), 3)
+    p_ref = po.encode(x)["OUTPUT_3DMM_PARAMS"]
+    t_dec = clock(lambda: (po.flame.vertices_3d(p_ref), po.flame.reprojected_vertices(p_ref)), 5)
+    frame = torch.randint(0, 256, (256, 256, 3), generator=torch.Generator().manual_seed(1), dtype=torch.uint8).numpy()
+    t_one = clock(lambda: po(frame), 3)
     out = {"value": sample * reps / dt, "unit": UNIT, "cores": cores, "kind": "port",
+           "split": {"encoder_heads_s": sample / t_enc, "decode_projection_heads_s": sample / t_dec,
+                     "single_image_call_ms": t_one * 1e3},
            "sample": f"{reps} passes of {sample} images (encoder + FLAME decode + projection), torch {torch.__version__} "
                      f"CPU fp32, {cores} of {os.cpu_count()} host threads (fastest of a small sweep)"}
     if parity_with is not None:
