@@ -171,6 +171,7 @@ class Dad3dEncoder:
                    "dad3d_encoder_create")
         self._h = h
         self._ws: Optional[Tensor] = None
+        self.ws_generation = 0          # bumped whenever the scratch buffer is reallocated (CUDA graphs bake in its address)
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -241,6 +242,7 @@ class Dad3dEncoder:
             _lib.check(-1, "dad3d_encoder_workspace_bytes")
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            self.ws_generation += 1
         with torch.cuda.device(self.device):
             _lib.check(self.lib.dad3d_encoder_forward(self._h, x.data_ptr(), B, params.data_ptr(), lms.data_ptr(),
                                                       heat.data_ptr() if heat is not None else None,

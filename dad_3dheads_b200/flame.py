@@ -88,6 +88,7 @@ class _Workspace:
 
     def __init__(self):
         self._buf: Dict[int, Tensor] = {}
+        self.generation = 0             # bumped on every reallocation (CUDA graphs bake in the buffer address)
 
     def get(self, device: torch.device, nbytes: int) -> Tensor:
         key = device.index if device.index is not None else torch.cuda.current_device()
@@ -95,6 +96,7 @@ class _Workspace:
         if buf is None or buf.numel() < nbytes:
             buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
             self._buf[key] = buf
+            self.generation += 1
         return buf
 
 
@@ -128,6 +130,10 @@ class FlameDecoder:
         self._h = h
         self.num_params = int(self.lib.dad3d_flame_num_params(h))
         self._ws = _Workspace()
+
+    @property
+    def ws_generation(self) -> int:
+        return self._ws.generation
 
     def __del__(self):
         h = getattr(self, "_h", None)

@@ -270,31 +270,161 @@ class FaceMeshPredictor:
             out[f"landmarks_{landmark_subset}"] = dec.gather(proj, self._landmark_index(landmark_subset))
         return out
 
+    def _ws_generation(self):
+        """Changes whenever the encoder or decoder scratch buffer is reallocated (captured graphs bake in its address)."""
+        dec = self.head_mesh.flame.decoder(self.device)
+        return (self.model.ws_generation, dec.ws_generation)
+
+    def _capture(self, static_in: Tensor, landmark_subset, to_2d, fast_decode):
+        """Warm up (plans, workspaces, tensor maps, index tables) and capture predict_batch(static_in) into a CUDA graph."""
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self.predict_batch(static_in, landmark_subset, to_2d, fast_decode)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = self.predict_batch(static_in, landmark_subset, to_2d, fast_decode)
+        return graph, out, self._ws_generation()
+
     def predict_batch_graphed(self, images: Tensor, landmark_subset: Optional[str] = "445", to_2d: bool = True,
                               fast_decode: bool = False) -> Dict[str, Tensor]:
         """:meth:`predict_batch` replayed from a CUDA graph (one graph per input shape / dtype / option set): the ~110 kernel
         launches of a step become one graph launch, which removes the launch gaps between the many sub-20 us layers.
         ``images`` is copied into the graph's static input buffer (host or device source); the returned tensors are the
-        graph's static outputs -- consume or clone them before the next call with the same signature."""
+        graph's static outputs -- consume or clone them before the next call with the same signature.
+
+        A captured graph holds raw pointers into the encoder / decoder scratch buffers.  Those buffers only ever grow; when a
+        later call (a larger batch, eager or graphed) reallocates one, every graph captured against the old buffer is
+        re-captured before it is replayed again (``_ws_generation``), so a stale pointer is never dereferenced."""
         assert isinstance(images, Tensor), "the graphed path takes one tensor ([B,3,S,S] fp32 or [B,H,W,3] uint8)"
         key = (tuple(images.shape), images.dtype, landmark_subset, to_2d, fast_decode)
         ent = self._graphs.get(key)
+        if ent is not None and ent[3] != self._ws_generation():
+            ent = None                                        # scratch moved since the capture: never replay it
+            self._graphs.pop(key)
         if ent is None:
             static_in = torch.empty(images.shape, dtype=images.dtype, device=self.device)
             static_in.copy_(images, non_blocking=True)
-            side = torch.cuda.Stream(self.device)
-            side.wait_stream(torch.cuda.current_stream(self.device))
-            with torch.cuda.stream(side):                     # warm-up: plans, workspaces, tensor maps, index tables
-                for _ in range(2):
-                    self.predict_batch(static_in, landmark_subset, to_2d, fast_decode)
-            torch.cuda.current_stream(self.device).wait_stream(side)
-            torch.cuda.synchronize(self.device)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                out = self.predict_batch(static_in, landmark_subset, to_2d, fast_decode)
-            ent = (graph, static_in, out)
+            graph, out, gen = self._capture(static_in, landmark_subset, to_2d, fast_decode)
+            ent = (graph, static_in, out, gen)
             self._graphs[key] = ent
-        graph, static_in, out = ent
+        graph, static_in, out, _ = ent
         static_in.copy_(images, non_blocking=True)
         graph.replay()
         return out
+
+    def open_stream(self, shape, dtype=torch.uint8, **kw) -> "BatchStream":
+        """A double-buffered pipeline over :meth:`predict_batch` for a fixed batch signature -- see :class:`BatchStream`."""
+        return BatchStream(self, shape, dtype, **kw)
+
+
+class BatchStream:
+    """Software pipeline around the graph replay of ``FaceMeshPredictor.predict_batch`` for one batch signature.
+
+    ``submit(images)`` enqueues, without blocking the host: the H2D copy of the (pinned) host batch on a copy stream, the
+    graph replay on the compute stream, the optional all-gather over ``group`` on a communication stream and the D2H copy of
+    the requested outputs into pinned host buffers on a fourth stream.  ``collect()`` blocks until the OLDEST submitted batch
+    has landed and returns its results.  With ``depth`` slots (default 2) the copies and the collective of batch i overlap
+    the encoder of batch i+1, so steady-state throughput is the compute time alone.  Results stay valid until ``depth`` more
+    batches have been submitted.
+    """
+
+    def __init__(self, predictor: FaceMeshPredictor, shape, dtype=torch.uint8, landmark_subset: Optional[str] = "445",
+                 to_2d: bool = True, fast_decode: bool = False, depth: int = 2,
+                 keys=("3dmm_params", "points", "3d_vertices", "landmarks_445"), host_results: bool = True,
+                 group=None, gather_keys=("3dmm_params", "3d_vertices", "landmarks_445")):
+        self.pred = predictor
+        dev = predictor.device
+        self.device = dev
+        self.depth = int(depth)
+        self.keys = tuple(keys)
+        self.host_results = host_results
+        self.group = group
+        self.gather_keys = tuple(gather_keys) if group is not None else ()
+        self.compute = torch.cuda.Stream(dev)
+        self.copy_in = torch.cuda.Stream(dev)
+        self.copy_out = torch.cuda.Stream(dev)
+        self.comm = torch.cuda.Stream(dev) if group is not None else None
+        self._args = (landmark_subset, to_2d, fast_decode)
+        self.slots = []
+        with torch.cuda.device(dev):
+            for _ in range(self.depth):
+                static_in = torch.zeros(tuple(shape), dtype=dtype, device=dev)
+                graph, out, gen = predictor._capture(static_in, *self._args)
+                slot = {"in": static_in, "graph": graph, "out": out, "gen": gen, "busy": False,
+                        "h2d": torch.cuda.Event(), "done": torch.cuda.Event(), "comm_done": torch.cuda.Event(),
+                        "d2h": torch.cuda.Event(), "gathered": {}, "host": {}}
+                if host_results:
+                    for k in self.keys:
+                        slot["host"][k] = torch.empty(out[k].shape, dtype=out[k].dtype).pin_memory()
+                if group is not None:
+                    import torch.distributed as dist
+                    world = dist.get_world_size(group)
+                    for k in self.gather_keys:
+                        t = out[k]
+                        slot["gathered"][k] = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype,
+                                                          device=dev)
+                self.slots.append(slot)
+            torch.cuda.synchronize(dev)
+        self._head = 0          # next slot to submit into
+        self._tail = 0          # oldest uncollected
+        self._inflight = 0
+
+    def submit(self, images: Tensor) -> None:
+        if self._inflight == self.depth:
+            raise RuntimeError("BatchStream: all slots in flight -- collect() before submitting more")
+        s = self.slots[self._head]
+        if s["gen"] != self.pred._ws_generation():           # scratch reallocated by another caller: re-capture this slot
+            torch.cuda.synchronize(self.device)
+            s["graph"], s["out"], s["gen"] = self.pred._capture(s["in"], *self._args)
+        with torch.cuda.stream(self.copy_in):
+            self.copy_in.wait_event(s["done"])               # the previous replay of this slot has consumed its input
+            s["in"].copy_(images, non_blocking=True)
+            s["h2d"].record(self.copy_in)
+        with torch.cuda.stream(self.compute):
+            self.compute.wait_event(s["h2d"])
+            self.compute.wait_event(s["d2h"])                # its previous results have left the device buffers
+            if self.comm is not None:
+                self.compute.wait_event(s["comm_done"])
+            s["graph"].replay()
+            s["done"].record(self.compute)
+        last = s["done"]
+        if self.comm is not None:
+            import torch.distributed as dist
+            with torch.cuda.stream(self.comm):
+                self.comm.wait_event(s["done"])
+                for k in self.gather_keys:
+                    dist.all_gather_into_tensor(s["gathered"][k], s["out"][k], group=self.group)
+                s["comm_done"].record(self.comm)
+            last = s["comm_done"]
+        with torch.cuda.stream(self.copy_out):
+            self.copy_out.wait_event(last)
+            if self.host_results:
+                for k in self.keys:
+                    s["host"][k].copy_(s["out"][k], non_blocking=True)
+            s["d2h"].record(self.copy_out)
+        s["busy"] = True
+        self._head = (self._head + 1) % self.depth
+        self._inflight += 1
+
+    def collect(self) -> Dict[str, Tensor]:
+        """Results of the oldest in-flight batch: pinned host tensors (``host_results``) or the slot's device outputs;
+        gathered tensors (when a group was given) under ``"gathered"``."""
+        if self._inflight == 0:
+            raise RuntimeError("BatchStream: nothing in flight")
+        s = self.slots[self._tail]
+        s["d2h"].synchronize()
+        s["busy"] = False
+        self._tail = (self._tail + 1) % self.depth
+        self._inflight -= 1
+        res = dict(s["host"]) if self.host_results else {k: s["out"][k] for k in self.keys}
+        if s["gathered"]:
+            res["gathered"] = s["gathered"]
+        return res
+
+    def drain(self) -> None:
+        while self._inflight:
+            self.collect()

@@ -1,4 +1,5 @@
-"""CPU restatement of the DAD-3DNet encoder ``FlameRegression.forward`` (TEST INFRASTRUCTURE ONLY; parity unpinned).
+"""CPU restatement of the DAD-3DNet encoder ``FlameRegression.forward`` (TEST INFRASTRUCTURE ONLY; pinned to the
+reference source by tests/test_oracle_pinned.py).
 
 Follows, line by line (paths relative to /root/reference):
   model_training/model/flame_regression.py:14-106   FlameHead, FusionLayer, ClassificationHead, FlameRegression.forward

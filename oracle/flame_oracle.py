@@ -1,6 +1,6 @@
 """CPU restatement of the reference's FLAME head decoder + weak-perspective projection (TEST INFRASTRUCTURE ONLY).
 
-Parity unpinned (see oracle/__init__.py): no reference test or golden vector exists for this path.
+Pinned against the unmodified reference source (oracle/ref_harness.py, tests/test_oracle_pinned.py).
 
 Each function cites the reference file:line (relative to /root/reference) it follows.  ``smplx.lbs`` (smplx==0.1.26,
 pinned in requirements.txt:17, NOT vendored in the reference tree) is restated from its published algorithm

@@ -1,4 +1,5 @@
-"""CPU restatement of ``predictor.FaceMeshPredictor`` (TEST INFRASTRUCTURE ONLY; parity unpinned -- oracle/__init__.py).
+"""CPU restatement of ``predictor.FaceMeshPredictor`` (TEST INFRASTRUCTURE ONLY; pinned to the reference
+source by tests/test_oracle_pinned.py).
 
 Follows /root/reference/predictor.py:78-203 with the restated encoder (oracle/encoder_oracle.py) standing in for the
 TorchScript module and the restated decoder (oracle/flame_oracle.py) for HeadMesh.  albumentations==1.0.0

@@ -180,14 +180,17 @@ def test_td_parity_launches_match(sd, cuda_device, monkeypatch):
     assert not bad, bad
 
 
-def test_encoder_golden_fixture(sd, cuda_device):
-    """tests/golden/encoder_golden.npz (tools/make_golden.py: fp64 oracle, weight seed 0, image seed 777)."""
+def test_encoder_reference_fixture(sd, cuda_device):
+    """tests/golden/reference_encoder.npz: outputs of the UNMODIFIED reference FlameRegression.forward
+    (tools/make_reference_golden.py; weight seed 0, image seed 777), fp64 run as the yard-stick."""
     import os
     import numpy as np
     from dad_3dheads_b200.encoder import Dad3dEncoder
-    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "encoder_golden.npz"))
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_encoder.npz"))
     x = torch.randn(2, 3, 256, 256, generator=torch.Generator().manual_seed(int(z["image_seed"])))
-    out = Dad3dEncoder(sd, cuda_device, precision="fp32")(x.to(cuda_device))
-    assert _rel(out[OUTPUT_3DMM_PARAMS], torch.from_numpy(z["params"])) < 3e-5
-    assert _rel(out[OUTPUT_2D_LANDMARKS], torch.from_numpy(z["landmarks"])) < 3e-5
-    assert _rel(out[OUTPUT_LANDMARKS_HEATMAP].sum(dim=(2, 3)), torch.from_numpy(z["heatmap_checksum"])) < 3e-5
+    for mode in ("fp32", "fp16x2"):
+        out = Dad3dEncoder(sd, cuda_device, precision=mode)(x.to(cuda_device))
+        assert _rel(out[OUTPUT_3DMM_PARAMS], torch.from_numpy(z["params_f64"])) < 3e-5, mode
+        assert _rel(out[OUTPUT_2D_LANDMARKS], torch.from_numpy(z["landmarks_f64"])) < 3e-5, mode
+        assert _rel(out[OUTPUT_LANDMARKS_HEATMAP].sum(dim=(2, 3)), torch.from_numpy(z["heatmap_sum_f64"])) < 3e-5, mode
+        assert _rel(out[OUTPUT_LANDMARKS_HEATMAP][:, :, :4, :4], torch.from_numpy(z["heatmap_corner_f64"])) < 1e-4, mode

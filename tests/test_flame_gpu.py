@@ -208,13 +208,21 @@ def test_empty_batch(head_mesh, cuda_device):
     assert v3.shape == (0, 5023, 3) and pj.shape == (0, 5023, 2)
 
 
-def test_golden_fixture(head_mesh, cuda_device):
+@pytest.mark.parametrize("B", [1, 6])
+def test_reference_fixture(head_mesh, cuda_device, B):
+    """tests/golden/reference_flame.npz: outputs of the UNMODIFIED reference HeadMesh (head_mesh.py:28-46) over its own
+    flame.pkl (tools/make_reference_golden.py), fp64 run as the yard-stick; north_star tolerance 1e-4, measured ~2e-7."""
     import os
-    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "flame_decode_golden.npz"))
-    p = torch.from_numpy(z["params"])
-    v3, pj = head_mesh.decode(p.to(cuda_device))
-    assert _rel(v3, torch.from_numpy(z["vertices3d"])) < 2e-6
-    assert _rel(pj, torch.from_numpy(z["projected"])) < 2e-6
-    dec = head_mesh.flame.decoder(cuda_device)
-    lm = dec.gather(pj, torch.from_numpy(z["idx445"].astype(np.int64)))
-    assert _rel(lm, torch.from_numpy(z["landmarks445"])) < 2e-6
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_flame.npz"))
+    p = torch.from_numpy(z[f"params_b{B}"])
+    v3, pj = head_mesh.decode(p.to(cuda_device), to_2d=False)
+    assert _rel(v3, torch.from_numpy(z[f"vertices3d_f64_b{B}"])) < 2e-6
+    assert _rel(pj, torch.from_numpy(z[f"projected3_f64_b{B}"])) < 2e-6
+    l2 = (v3.double().cpu() - torch.from_numpy(z[f"vertices3d_f64_b{B}"])).norm(dim=-1).max().item()
+    assert l2 < 1e-6, l2                                        # per-vertex L2 in metres (target < 1e-4)
+    vz = head_mesh.vertices_3d(p.to(cuda_device), zero_rotation=True)
+    assert _rel(vz, torch.from_numpy(z[f"vertices3d_zero_rot_f32_b{B}"])) < 2e-6
+    q = p.clone()
+    pr = head_mesh.reprojected_vertices(q, to_2d=False)         # CPU tensor in -> CPU out, tz zeroed through the view
+    assert _rel(pr, torch.from_numpy(z[f"projected3_f64_b{B}"])) < 2e-6
+    assert np.array_equal(q.numpy(), z[f"params_after_reproject_f32_b{B}"])

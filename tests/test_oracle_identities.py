@@ -1,5 +1,5 @@
-"""The oracle has no reference golden vectors to be pinned against ("parity unpinned"), so it is checked
-against closed-form identities of the FLAME decoder instead (SURVEY §8c last row of the fixtures entry)."""
+"""Closed-form identities of the FLAME decoder the oracle must satisfy (SURVEY §8c last row of the fixtures entry).  These
+complement tests/test_oracle_pinned.py, which pins the oracle to the reference's own source."""
 import numpy as np
 import torch
 

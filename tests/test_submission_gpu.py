@@ -51,3 +51,24 @@ def test_submission_fields(cuda_device, tmp_path):
     SubmissionWriter.save(sub, str(tmp_path / "sub.json"))
     import json
     assert set(json.load(open(tmp_path / "sub.json"))) == {"a", "b", "c"}
+
+
+def test_submission_2d_landmarks_are_in_original_image_pixels(cuda_device):
+    """Non-square, non-256 inputs: "68_landmarks_2d" must be in ORIGINAL-image pixels (what benchmark.py:86-99 compares with
+    its ground truth).  Oracle route = the reference's: per image, predictor.__call__ semantics (readjust the 3DMM vector to
+    the input image, then reprojected_vertices) followed by the barycentric 68 embedding on those projected vertices."""
+    from dad_3dheads_b200.predictor import FaceMeshPredictor
+    from dad_3dheads_b200.submission import SubmissionWriter
+    sd = synthetic_state_dict(0)
+    st = load_static()
+    pred = FaceMeshPredictor.dad_3dnet(state_dict=sd)
+    sw = SubmissionWriter(pred)
+    g = np.random.default_rng(3)
+    imgs = [g.integers(0, 256, s + (3,), dtype=np.uint8) for s in ((300, 517), (641, 203), (256, 256))]
+    sub = sw.predict(imgs, ["a", "b", "c"])
+    orc = PredictorOracle(sd, dtype=torch.float64)
+    for key, img in zip(["a", "b", "c"], imgs):
+        want = orc(img)                                        # projected_vertices in input-image pixels (predictor.py:137)
+        lm2 = _oracle_68(want["projected_vertices"][0], st)
+        got2 = torch.tensor(sub[key]["68_landmarks_2d"], dtype=torch.float64)
+        assert (got2 - lm2).abs().max() < 0.1, (key, (got2 - lm2).abs().max())          # pixels of a ~500-px image
