@@ -13,6 +13,8 @@ DAD3D_BLEND_FAST = 4
 DAD3D_BLEND_SIMT = 8
 DAD3D_DECODE_UNFUSED = 16
 DAD3D_DECODE_CLUSTER = 32
+DAD3D_BLEND_HILO = 64
+DAD3D_DECODE_PAIR = 128
 
 
 class Dad3dError(RuntimeError):

@@ -8,11 +8,13 @@
 // model_training/head_mesh.py:33-46.  See DESIGN.md for layouts and rooflines.
 #include <cuda_fp16.h>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
 #include "../../include/dad3d.h"
 #include "common.h"
+#include "flame_decode.cuh"
 #include "tile_gemm.cuh"
 #include "tmap.h"
 
@@ -489,7 +491,9 @@ using namespace dad3d;
 
 struct dad3d_flame {
   int device = 0;
-  int smem_configured[2] = {0, 0};           // per handle (= per device): max dynamic smem set for <EpiLbs> / <EpiBlend>
+  int smem_configured[4] = {0, 0, 0, 0};     // per handle (= per device): max dynamic smem set for <EpiLbs> / <EpiBlend> /
+                                             // flame_decode_kernel<false> / <true>
+  int max_clusters[2] = {0, 0};              // per handle: co-resident clusters (2x2 tile-engine clusters / decode CTA pairs)
   int nv = 0, n3 = 0, npad = 0;
   int num_sms = 0;
   FlameLayoutDev layout{};
@@ -503,6 +507,7 @@ struct dad3d_flame {
   CUtensorMap map_b[2];                      // box 64 x 128 (unfused path)
   CUtensorMap map_b96[2];                    // box 64 x 96  (fused path)
   CUtensorMap map_b48[2];                    // box 64 x 48  (fused path, 2x2 clusters: each CTA loads half of a B tile)
+  CUtensorMap map_dec[2];                    // hi plane, box 64 x 192 (decode kernel) / 64 x 96 (its CTA-pair variant)
   int fused_chunk = 0;                       // heads per pass of the fused path: 4 row tiles per SM
 };
 
@@ -510,7 +515,7 @@ namespace {
 
 template <class Epi>
 int launch_tile_gemm(const GemmMaps& maps, const GemmGeom& g, const typename Epi::Params& ep, int num_sms,
-                     cudaStream_t stream, int* configured) {
+                     cudaStream_t stream, int* configured, int* max_clusters_cache) {
   // function attributes are per device: remembered in the handle, not in a process-wide static
   const int smem = gemm_smem_bytes(g, Epi::kExtraSmemBytes);
   if (!*configured) {
@@ -532,8 +537,8 @@ int launch_tile_gemm(const GemmMaps& maps, const GemmGeom& g, const typename Epi
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.numAttrs = 1;
-    static int max_clusters = 0;                       // co-resident clusters of this size (GPC packing: < #SM / csize)
-    if (max_clusters == 0) {
+    int& max_clusters = *max_clusters_cache;           // co-resident clusters of this size (GPC packing: < #SM / csize);
+    if (max_clusters == 0) {                           // cached in the handle: occupancy is a per-device property
       cfg.gridDim = dim3(num_sms / csize * csize);
       DAD3D_CUDA_OK(cudaOccupancyMaxActiveClusters(&max_clusters, tile_gemm_kernel<Epi>, &cfg));
       if (max_clusters < 1) { set_error("no co-resident cluster fits"); return DAD3D_ERR_CUDA; }
@@ -549,6 +554,113 @@ int launch_tile_gemm(const GemmMaps& maps, const GemmGeom& g, const typename Epi
   count_launch();
   DAD3D_CUDA_OK(cudaGetLastError());
   return DAD3D_OK;
+}
+
+template <bool kPair>
+int decode_groups_max(dad3d_flame* h);
+
+// One launch of flame_decode_kernel over `rows` heads whose fp16 coefficient rows (a_hi) and transform records (xf) the prep
+// kernel has written.
+template <bool kPair>
+int launch_flame_decode(dad3d_flame* h, const __half* a_hi, int rows, const float* xf, float* v3, float* pj, int pc,
+                        float image_size, cudaStream_t stream) {
+  int* configured = &h->smem_configured[kPair ? 3 : 2];
+  if (!*configured) {
+    DAD3D_CUDA_OK(cudaFuncSetAttribute(flame_decode_kernel<kPair>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecSmemLimit));
+    *configured = 1;
+  }
+  CUtensorMap map_a;
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(kKPad), static_cast<uint64_t>(rows)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(kKPad) * 2};
+    const uint32_t box[2] = {kDecBlockK, kDecBlockM};
+    if (!make_tmap_16bit(&map_a, a_hi, 2, dims, strides, box, nullptr)) return DAD3D_ERR_CUDA;
+  }
+  DecodeParams p;
+  p.rows = rows;
+  p.nv = h->nv;
+  p.n_tiles = ceil_div(h->n3, kDecN);
+  const int m_tiles = ceil_div(rows, kDecBlockM);
+  p.m_units = kPair ? ceil_div(m_tiles, 2) : m_tiles;
+  const int groups_max = decode_groups_max<kPair>(h);
+  if (groups_max < 1) return DAD3D_ERR_CUDA;
+  // fewer row tiles than SMs: split every row tile's sweep over the vertex tiles so that all SMs get work
+  p.splits = p.m_units >= groups_max ? 1 : ceil_div(groups_max, p.m_units);
+  if (p.splits > p.n_tiles) p.splits = p.n_tiles;
+  const int units = p.m_units * p.splits;
+  const int groups = units < groups_max ? units : groups_max;
+  {
+    // ring geometry: k-blocks per slot (fewer, longer slots amortise the per-slot barrier round trip) -- A/B via environment
+    const char* e = std::getenv("DAD3D_DECODE_KBS");
+    int kbs = e ? std::atoi(e) : (kPair ? 2 : 1);
+    if (kbs < 1) kbs = 1;
+    if (kbs > 4) kbs = 4;
+    while (kbs > 1 && dec_max_stages<kPair>(kbs) < 2) --kbs;
+    p.kbs = kbs;
+    p.stages = dec_max_stages<kPair>(kbs);
+  }
+  p.xf = xf;
+  p.w2 = h->d_w2;
+  p.verts3d = v3;
+  p.proj = pj;
+  p.pc = pc;
+  p.image_size = image_size;
+  {
+    const char* e = std::getenv("DAD3D_DECODE_DEBUG");
+    p.debug = e ? std::atoi(e) : 0;
+    const char* e2 = std::getenv("DAD3D_DECODE_POLL");
+    p.poll = e2 ? std::atoi(e2) : 0;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3(kDecThreads);
+  cfg.gridDim = dim3(groups * (kPair ? 2 : 1));
+  cfg.dynamicSmemBytes = dec_smem_bytes<kPair>(p.stages, p.kbs);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  cfg.attrs = attr;
+  cfg.numAttrs = 0;
+  if (kPair) {
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.numAttrs = 1;
+  }
+  DAD3D_CUDA_OK(cudaLaunchKernelEx(&cfg, flame_decode_kernel<kPair>, map_a, h->map_dec[kPair ? 1 : 0], p));
+  count_launch();
+  DAD3D_CUDA_OK(cudaGetLastError());
+  return DAD3D_OK;
+}
+
+template <>
+int decode_groups_max<false>(dad3d_flame* h) { return h->num_sms; }
+template <>
+int decode_groups_max<true>(dad3d_flame* h) {
+  if (h->max_clusters[1] == 0) {                       // co-resident CTA pairs (GPC packing may leave a few SMs unpaired)
+    if (!h->smem_configured[3]) {
+      if (cudaFuncSetAttribute(flame_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecSmemLimit) != cudaSuccess)
+        return 0;
+      h->smem_configured[3] = 1;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.blockDim = dim3(kDecThreads);
+    cfg.gridDim = dim3(h->num_sms / 2 * 2);
+    cfg.dynamicSmemBytes = dec_smem_bytes<true>(dec_max_stages<true>(2), 2);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, flame_decode_kernel<true>, &cfg) != cudaSuccess || n < 1) {
+      set_error("no co-resident CTA pair fits");
+      return 0;
+    }
+    h->max_clusters[1] = n;
+  }
+  return h->max_clusters[1];
 }
 
 inline unsigned short f32_to_f16_bits(float x) {
@@ -669,7 +781,10 @@ int dad3d_flame_create(dad3d_flame** out, const float* shapedirs_h, const float*
     w2[2 * i] = rest;
     w2[2 * i + 1] = lbs_weights_h[static_cast<size_t>(i) * kJoints + 2];
   }
-  h->jaw_only = (lay->neck == 0 && lay->eyeballs == 0);
+  // the two-transform epilogue is exact only when every non-jaw joint carries joint 0's transform: no neck / eyeball pose in
+  // the layout AND the FLAME kinematic tree (jaw = joint 2, child of the neck, with no children of its own)
+  h->jaw_only = (lay->neck == 0 && lay->eyeballs == 0 && parents_h[1] == 0 && parents_h[2] == 1 && parents_h[3] == 1 &&
+                 parents_h[4] == 1);
 
   // folded joint regressor: J = Jreg * T + (Jreg * S) beta   (smplx vertices2joints applied to v_shaped)
   std::vector<float> jt(15, 0.f), jdirsT(15 * kBetas, 0.f);
@@ -716,6 +831,14 @@ int dad3d_flame_create(dad3d_flame** out, const float* shapedirs_h, const float*
     const uint32_t box48[2] = {kBlockK, kFusedBlockN / 2};
     if (!make_tmap_16bit(&h->map_b48[p], h->d_basis[p], 2, dims, strides, box48, nullptr)) return fail(DAD3D_ERR_CUDA);
   }
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(kKPad), static_cast<uint64_t>(npad)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(kKPad) * 2};
+    const uint32_t box192[2] = {kDecBlockK, kDecN};
+    const uint32_t box96h[2] = {kDecBlockK, kDecN / 2};
+    if (!make_tmap_16bit(&h->map_dec[0], h->d_basis[0], 2, dims, strides, box192, nullptr)) return fail(DAD3D_ERR_CUDA);
+    if (!make_tmap_16bit(&h->map_dec[1], h->d_basis[0], 2, dims, strides, box96h, nullptr)) return fail(DAD3D_ERR_CUDA);
+  }
   h->fused_chunk = h->num_sms * kBlockM * 4;
   *out = h;
   return DAD3D_OK;
@@ -756,9 +879,17 @@ int dad3d_flame_decode(dad3d_flame* h, const float* params_d, int32_t B, int32_t
   DAD3D_REQUIRE(B > 0 && params_d, "params");
   DAD3D_REQUIRE(vertices3d_d || projected_d, "at least one output must be requested");
   DAD3D_REQUIRE(workspace_d && workspace_bytes >= dad3d_flame_workspace_bytes(h, B), "workspace too small");
-  DAD3D_REQUIRE((reinterpret_cast<uintptr_t>(workspace_d) & 1023) == 0 || true, "workspace alignment");
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   const bool fused = h->jaw_only && !(flags & (DAD3D_BLEND_SIMT | DAD3D_DECODE_UNFUSED));
+  // default: the dedicated one-product decode kernel (flame_decode.cuh); DAD3D_BLEND_HILO = 3-product hi/lo operands through
+  // the tile engine (fp32-class blend product).  DAD3D_BLEND_FAST is the old name of today's default and is accepted as a no-op.
+  const bool dedicated = fused && !(flags & DAD3D_BLEND_HILO);
+  bool pair = false;
+  if (dedicated) {
+    const char* env = std::getenv("DAD3D_DECODE_PAIR");         // A/B switch: 1 = CTA pairs for big batches, 0 = never
+    const int want = (flags & DAD3D_DECODE_PAIR) ? 1 : (env ? std::atoi(env) : 0);
+    pair = want > 0 && ceil_div(B, kDecBlockM) >= 2 * h->num_sms;
+  }
   const int chunk = fused ? h->fused_chunk : kDecodeChunk;
   const int rows_max = B < chunk ? B : chunk;
   uint8_t* ws = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(workspace_d), 1024));
@@ -782,7 +913,11 @@ int dad3d_flame_decode(dad3d_flame* h, const float* params_d, int32_t B, int32_t
       count_launch();
       DAD3D_CUDA_OK(cudaGetLastError());
     }
-    if (flags & DAD3D_BLEND_SIMT) {
+    if (dedicated) {
+      int rc = pair ? launch_flame_decode<true>(h, a_hi, rows, xf, v3, pj, pc, image_size, stream)
+                    : launch_flame_decode<false>(h, a_hi, rows, xf, v3, pj, pc, image_size, stream);
+      if (rc != DAD3D_OK) return rc;
+    } else if (flags & DAD3D_BLEND_SIMT) {
       dim3 grid(ceil_div(h->npad, 256), rows);
       blend_simt_kernel<<<grid, 256, 0, stream>>>(a_hi, a_lo, h->d_basis[0], h->d_basis[1], rows, h->npad, vposed);
       count_launch();
@@ -816,7 +951,7 @@ int dad3d_flame_decode(dad3d_flame* h, const float* params_d, int32_t B, int32_t
       g.n_tiles = ceil_div(h->n3, block_n);
       g.block_n = block_n;
       g.fmt16 = 0;
-      if (flags & DAD3D_BLEND_FAST) {
+      if ((flags & DAD3D_BLEND_FAST) && !(flags & DAD3D_BLEND_HILO)) {      // unfused A/B path with one product
         g.nA = 1; g.nB = 1; g.n_mma = 1; g.mma_a[0] = 0; g.mma_b[0] = 0; g.mma_acc[0] = 0; g.n_acc = 1;
       } else {
         g.nA = 2; g.nB = 2; g.n_mma = 3; g.n_acc = 2;
@@ -828,13 +963,13 @@ int dad3d_flame_decode(dad3d_flame* h, const float* params_d, int32_t B, int32_t
         g.sched = g.tiles_w >= h->num_sms ? 1 : 0;          // enough row tiles to give every SM its own
         g.stages = gemm_max_stages(g, EpiLbs::kExtraSmemBytes);
         EpiLbs::Params ep{xf, h->d_w2, h->nv, v3, pj, pc, image_size};
-        int rc = launch_tile_gemm<EpiLbs>(maps, g, ep, h->num_sms, stream, &h->smem_configured[0]);
+        int rc = launch_tile_gemm<EpiLbs>(maps, g, ep, h->num_sms, stream, &h->smem_configured[0], &h->max_clusters[0]);
         if (rc != DAD3D_OK) return rc;
       } else {
         g.sched = 0;
         g.stages = gemm_max_stages(g);
         EpiBlend::Params ep{vposed, h->npad};
-        int rc = launch_tile_gemm<EpiBlend>(maps, g, ep, h->num_sms, stream, &h->smem_configured[1]);
+        int rc = launch_tile_gemm<EpiBlend>(maps, g, ep, h->num_sms, stream, &h->smem_configured[1], &h->max_clusters[0]);
         if (rc != DAD3D_OK) return rc;
       }
     }

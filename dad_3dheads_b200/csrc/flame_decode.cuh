@@ -1,0 +1,496 @@
+// Dedicated FLAME decode kernel for sm_100a (the default path of dad3d_flame_decode):
+//
+//   vertices[h, v, :] = skin( T + S beta_h + P theta_h )                 flame.py:182-229, smplx.lbs, model/utils.py:92-101
+//
+// as ONE persistent tcgen05 kernel: blend shapes + pose correctives + template as a [heads,448] x [15069,448]^T fp16 GEMM
+// (fp32 accumulate in TMEM; the template rides in two K columns and is exact to 22 bits), followed in the epilogue by
+// linear-blend skinning, the z offset, the 6-DoF rotation and the weak-perspective projection (head_mesh.py:33-46), written
+// straight into the reference's [B,5023,3] / [B,5023,2|3] layouts.
+//
+// Why not the generic tile engine (tile_gemm.cuh, still used by the strict hi/lo mode): measured there, the main loop is
+// bound by SHARED-MEMORY bandwidth, not by the tensor pipe -- every k-block re-streams the 128-head coefficient tile
+// (16 KiB) next to the basis tile, and every 128x96x16 MMA re-reads 7 KiB of operands in its 48 cycles.  This kernel is
+// built around bytes per MMA cycle instead:
+//   * the coefficient tile of a row tile (128 heads x 448 x fp16 = 112 KiB) is loaded ONCE and stays resident in shared
+//     memory while the CTA sweeps its range of vertex tiles (A-stationary); only the basis streams (TMA ring);
+//   * vertex tiles are 192 columns (64 vertices) wide: 10 KiB of operand reads per 96-cycle MMA instead of 7 KiB per 48;
+//   * CTA pairs (cta_group::2, kPair): the pair shares one 192-column basis tile, each CTA loading and holding half of it,
+//     so basis bytes through each SM's shared memory halve again (M = 256 heads per pair);
+//   * one tensor-core product per MAC (fp16 operands, 11-bit mantissa like TF32; the power-of-two pre-scaled basis keeps
+//     every operand normal).  Measured error of the vertices against the fp64 reference: relL2 1.5e-5, inside the 1e-4
+//     contract; the 3-product hi/lo mode (2e-7) remains available as DAD3D_BLEND_HILO through the tile engine.
+// Roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer (one elected lane), warps 2..9 epilogue -- warp w owns TMEM
+// lanes 32*(w%4).. (= heads) and column group (w-2)/4 (96 columns = 32 vertices), processed as 4 passes of 8 vertices:
+// TMEM -> registers -> skinning with two register-resident transforms per head and per-vertex (w_rest, w_jaw) broadcast
+// from a lane-distributed table (warp-uniform branches skip the jaw / rest transform where its weight is zero) -> per-warp
+// staging tile -> coalesced 128-byte global stores (the 60 276-byte row pitch of [B,5023,3] rules out TMA stores).
+// Two TMEM accumulator buffers (2 x 192 columns): the epilogue of tile i overlaps the MMAs of tile i+1.
+#pragma once
+#include "ptx.cuh"
+
+namespace dad3d {
+
+constexpr int kDecBlockM = 128;
+constexpr int kDecBlockK = 64;
+constexpr int kDecN = 192;                         // columns per vertex tile = 64 vertices
+constexpr int kDecKBlocks = 7;                     // 448 / 64
+constexpr int kDecABytes = kDecBlockM * kDecBlockK * 2;          // 16 KiB per k-block of the coefficient tile
+constexpr int kDecAResident = kDecKBlocks * kDecABytes;           // 112 KiB
+constexpr int kDecThreads = 320;
+constexpr int kDecEpiWarps = 8;
+constexpr int kDecPassCols = 24;                   // 8 vertices per pass
+constexpr int kDecCarry = 8;                       // floats of the previous pass kept in front of each staged row
+constexpr int kDecStagePitch = 36;                 // floats per staged row: 8 carry + 24 new + 4 pad (144 B: conflict-free STS.128)
+constexpr int kDecStageBytes = 32 * kDecStagePitch * 4;           // 3584 B per epilogue warp
+constexpr int kDecXfFloats = 68;
+constexpr int kDecSmemLimit = 227 * 1024;
+
+struct DecodeParams {
+  int rows;                 // heads in this launch
+  int nv;                   // vertices (5023)
+  int n_tiles;              // ceil(3*nv / 192)
+  int m_units;              // row tiles (non-pair) or row-tile pairs (pair)
+  int splits;               // each m unit is split into `splits` contiguous ranges of vertex tiles
+  int stages;               // depth of the basis ring (slots)
+  int kbs;                  // k-blocks per ring slot (1..4): one full/empty barrier round trip per slot
+  const float* xf;          // [rows][68] per-head transform records (flame_prep_kernel)
+  const float* w2;          // [nv][2] (w_rest, w_jaw)
+  float* verts3d;           // [rows][nv][3] or null
+  float* proj;              // [rows][nv][pc] or null
+  int pc;
+  float image_size;
+  int poll;                 // 1: producer / MMA warps poll their barriers with test_wait instead of try_wait (A/B)
+  int debug;                // diagnostics only (DAD3D_DECODE_DEBUG): 1 = all global stores go to the first 128 rows (L2-resident
+                            // footprint: isolates the SM -> L2 store path from DRAM), 2 = stores predicated off at run time, 3 = the epilogue only
+                            // hands the accumulator back (pure main-loop rate)
+};
+
+template <bool kPair>
+__host__ __device__ inline int dec_b_stage_bytes() { return (kPair ? kDecN / 2 : kDecN) * kDecBlockK * 2; }
+template <bool kPair>
+__host__ inline int dec_max_stages(int kbs) {
+  const int fixed = kDecAResident + kDecEpiWarps * kDecStageBytes + 1024 + 512;
+  int s = (kDecSmemLimit - fixed) / (kbs * dec_b_stage_bytes<kPair>());
+  return s > 8 ? 8 : s;
+}
+template <bool kPair>
+__host__ inline int dec_smem_bytes(int stages, int kbs) {
+  return kDecAResident + stages * kbs * dec_b_stage_bytes<kPair>() + kDecEpiWarps * kDecStageBytes + 1024 + 512;
+}
+
+// unit u of this CTA (pair): row tile (pair) m, vertex tiles [n0, n1)
+__device__ __forceinline__ bool dec_unit_at(const DecodeParams& p, int group, int n_groups, int i, int* m, int* n0, int* n1) {
+  const int u = group + i * n_groups;
+  if (u >= p.m_units * p.splits) return false;
+  *m = u / p.splits;
+  const int part = u - *m * p.splits;
+  *n0 = static_cast<int>(static_cast<long long>(part) * p.n_tiles / p.splits);
+  *n1 = static_cast<int>(static_cast<long long>(part + 1) * p.n_tiles / p.splits);
+  return true;
+}
+
+// ---- sector-aligned stores.  Rows of the reference layout are only 4-byte aligned (pitch 60 276 B), and a store that covers
+// part of a 32-byte sector costs the L2 a read-modify-write (measured: 24.4 M heads/s with runs cut at arbitrary offsets,
+// 37.3 M with sector-aligned runs).  Each staged row therefore keeps the last 8 floats of the previous pass in front of the
+// 24 new ones (staged positions [0,8) | [8,32)), and row r is written as the window of 24 floats that starts
+// c_r = (address of the pass's first float of row r, in floats) mod 8 floats EARLIER: 3 whole, aligned sectors.  c_r depends
+// on the row only (every pass advances a row by exactly 3 sectors).  The first pass of a warp's column range has no carry
+// (head elements are predicated off: one partial sector per 96 columns), the last pass also writes the c_r-float tail.
+//
+// Hot path: columns [0,16) of the window leave as 16 warp stores of 2 rows x 16 floats, columns [16,24) as 8 warp stores of
+// 4 rows x 8 floats; shared-memory loads are issued eight at a time ahead of the global stores they feed.  `cb` = (address
+// of row 0's first new float, in floats) mod 8, `rho` = row pitch mod 8.
+template <int RUN>
+__device__ __forceinline__ void dec_flush_aligned(float* __restrict__ dst, unsigned pitch, const float* __restrict__ stage, int lane,
+                                                  unsigned cb, unsigned rho, bool head, bool tail) {
+  const int off_min = head ? 0 : -kDecCarry;          // first pass of a column range: nothing in front of the new floats
+  {
+    const int rl = (lane >> 4) * 4, c0 = lane & 15;
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      float t[8];
+      int off[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int row = (((8 * g + u) >> 2) * 8 + ((8 * g + u) & 3)) + rl;      // rows rl + {0..3, 8..11, 16..19, 24..27}
+        const int c = static_cast<int>((cb + rho * row) & 7u);
+        off[u] = c0 - c;                                                        // column relative to the pass's first new float
+        t[u] = stage[row * kDecStagePitch + kDecCarry + off[u]];
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int row = (((8 * g + u) >> 2) * 8 + ((8 * g + u) & 3)) + rl;
+        if (off[u] >= off_min) dst[static_cast<size_t>(row) * pitch + off[u]] = t[u];
+      }
+    }
+  }
+  {
+    constexpr int kW = RUN - 16;                       // 8 columns [16,24) of a 24-float run; a 16-float run has none
+    if (kW > 0) {
+      const int rl = (lane >> 3) * 2, c0 = 16 + (lane & 7);
+      float t[8];
+      int off[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int row = ((u >> 1) * 8 + (u & 1)) + rl;                          // rows rl + {0,1, 8,9, 16,17, 24,25}
+        const int c = static_cast<int>((cb + rho * row) & 7u);
+        off[u] = c0 - c;
+        t[u] = stage[row * kDecStagePitch + kDecCarry + off[u]];
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int row = ((u >> 1) * 8 + (u & 1)) + rl;
+        dst[static_cast<size_t>(row) * pitch + off[u]] = t[u];
+      }
+    }
+  }
+  if (tail) {                                          // the last c_r floats of the warp's column range (c_r < 8): 4 rows per store
+    const int rl = lane >> 3, k = lane & 7;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int row = 4 * u + rl;
+      const int c = static_cast<int>((cb + rho * row) & 7u);
+      if (k < c) dst[static_cast<size_t>(row) * pitch + RUN - c + k] = stage[row * kDecStagePitch + kDecCarry + RUN - c + k];
+    }
+  }
+}
+// Edge tiles (last row tile of the batch, last vertex tile of the mesh): plain predicated loop, one row per warp store, no
+// carry (the staged new floats [8, 8 + RUN) of each row go out as they are).
+template <int RUN>
+__device__ __noinline__ void dec_flush_edge(float* __restrict__ dst, unsigned pitch, const float* __restrict__ stage, int lane,
+                                            int rows_valid, int cols_valid) {
+  if (lane < cols_valid && lane < RUN)
+    for (int r = 0; r < rows_valid && r < 32; ++r)
+      dst[static_cast<size_t>(r) * pitch + lane] = stage[r * kDecStagePitch + kDecCarry + lane];
+}
+
+__device__ __forceinline__ void dec_wait(uint64_t* bar, uint32_t parity, int poll) {
+  if (poll) ptx::mbar_wait_poll(bar, parity);
+  else ptx::mbar_wait(bar, parity);
+}
+
+template <bool kPair>
+__global__ void __launch_bounds__(kDecThreads, 1)
+flame_decode_kernel(const __grid_constant__ CUtensorMap map_a,     // coefficients [rows, 448] fp16, box 64 x 128
+                    const __grid_constant__ CUtensorMap map_b,     // basis [npad, 448] fp16, box 64 x (192 | 96)
+                    const DecodeParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr int kBBlock = (kPair ? kDecN / 2 : kDecN) * kDecBlockK * 2;   // one k-block of (my half of) a basis tile
+  const int kBStage = p.kbs * kBBlock;                             // one ring slot = p.kbs k-blocks
+  uint8_t* smem_a = smem;                                          // [7][16 KiB] resident coefficient tile
+  uint8_t* smem_b = smem + kDecAResident;                          // [stages][kBStage]
+  uint8_t* stage_out = smem_b + p.stages * kBStage;                // [8][3584 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_out + kDecEpiWarps * kDecStageBytes);
+  uint64_t* full_bar = bars;                  // [8]  basis ring
+  uint64_t* empty_bar = bars + 8;             // [8]
+  uint64_t* afull_bar = bars + 16;            // [7]  one per k-block of the resident coefficient tile
+  uint64_t* aempty_bar = bars + 23;           // [1]  all MMAs of the unit have read it
+  uint64_t* tfull_bar = bars + 24;            // [2]
+  uint64_t* tempty_bar = bars + 26;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
+
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int crank = kPair ? static_cast<int>(ptx::cluster_ctarank()) : 0;
+  const int group = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int n_groups = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&map_a);
+    ptx::prefetch_tmap(&map_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < 8; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int k = 0; k < kDecKBlocks; ++k) ptx::mbar_init(&afull_bar[k], 1);
+    ptx::mbar_init(aempty_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(&tfull_bar[b], 1);
+      ptx::mbar_init(&tempty_bar[b], (kPair ? 2 : 1) * kDecEpiWarps * 32);   // pair: both CTAs' epilogues release the leader's
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 0) {
+    if constexpr (kPair) { ptx::tmem_alloc_2sm(tmem_slot, 512); ptx::tmem_relinquish_2sm(); }
+    else { ptx::tmem_alloc(tmem_slot, 512); ptx::tmem_relinquish(); }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if constexpr (kPair) ptx::cluster_sync_all();     // the peer's barriers exist before anyone signals them
+  ptx::grid_dep_launch();
+  ptx::grid_dep_wait();
+
+  if (warp == 0) {
+    // ===================================================== TMA producer (whole warp walks the schedule, one lane issues)
+    int stage = 0;
+    uint32_t phase = 0, aphase = 0;
+    int m, n0, n1;
+    for (int ui = 0; dec_unit_at(p, group, n_groups, ui, &m, &n0, &n1); ++ui) {
+      // the resident coefficient tile may be overwritten once every MMA of the previous unit has read it
+      dec_wait(aempty_bar, aphase ^ 1u, p.poll);
+      const int row0 = (kPair ? 2 * m + crank : m) * kDecBlockM;
+      if (ptx::elect_one_sync()) {
+        for (int kb = 0; kb < kDecKBlocks; ++kb) {
+          if constexpr (kPair) {
+            const uint32_t lead = ptx::mapa_u32(&afull_bar[kb], 0);
+            if (crank == 0) ptx::mbar_expect_tx(&afull_bar[kb], 2 * kDecABytes);
+            ptx::tma_load_2d_2sm(smem_a + kb * kDecABytes, &map_a, lead, kb * kDecBlockK, row0);
+          } else {
+            ptx::mbar_expect_tx(&afull_bar[kb], kDecABytes);
+            ptx::tma_load_2d(smem_a + kb * kDecABytes, &map_a, &afull_bar[kb], kb * kDecBlockK, row0);
+          }
+        }
+      }
+      __syncwarp();
+      aphase ^= 1u;
+      for (int n = n0; n < n1; ++n) {
+        for (int kb0 = 0; kb0 < kDecKBlocks; kb0 += p.kbs) {
+          const int nk = min(p.kbs, kDecKBlocks - kb0);
+          dec_wait(&empty_bar[stage], phase ^ 1u, p.poll);
+          if (ptx::elect_one_sync()) {
+            if constexpr (kPair) {
+              const uint32_t lead = ptx::mapa_u32(&full_bar[stage], 0);
+              if (crank == 0) ptx::mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(2 * nk * kBBlock));
+              for (int j = 0; j < nk; ++j)
+                ptx::tma_load_2d_2sm(smem_b + stage * kBStage + j * kBBlock, &map_b, lead, (kb0 + j) * kDecBlockK,
+                                     n * kDecN + crank * (kDecN / 2));
+            } else {
+              ptx::mbar_expect_tx(&full_bar[stage], static_cast<uint32_t>(nk * kBBlock));
+              for (int j = 0; j < nk; ++j)
+                ptx::tma_load_2d(smem_b + stage * kBStage + j * kBBlock, &map_b, &full_bar[stage], (kb0 + j) * kDecBlockK,
+                                 n * kDecN);
+            }
+          }
+          __syncwarp();
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    if (!kPair || crank == 0) {
+      const uint32_t idesc = ptx::make_idesc_f16(0u, kPair ? 2 * kDecBlockM : kDecBlockM, kDecN);
+      int stage = 0;
+      uint32_t phase = 0, aphase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      int m, n0, n1;
+      for (int ui = 0; dec_unit_at(p, group, n_groups, ui, &m, &n0, &n1); ++ui) {
+        for (int n = n0; n < n1; ++n) {
+          dec_wait(&tempty_bar[acc], acc_phase ^ 1u, p.poll);
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kDecN);
+          for (int kb0 = 0; kb0 < kDecKBlocks; kb0 += p.kbs) {
+            const int nk = min(p.kbs, kDecKBlocks - kb0);
+            if (n == n0)                                             // first sweep over the freshly loaded coefficient tile
+              for (int j = 0; j < nk; ++j) dec_wait(&afull_bar[kb0 + j], aphase, p.poll);
+            dec_wait(&full_bar[stage], phase, p.poll);
+            ptx::tc_fence_after();
+            const uint32_t sa0 = ptx::smem_u32(smem_a + kb0 * kDecABytes);
+            const uint32_t sb0 = ptx::smem_u32(smem_b + stage * kBStage);
+            const bool last = kb0 + nk == kDecKBlocks;
+            if (ptx::elect_one_sync()) {
+              for (int j = 0; j < nk; ++j) {
+                const uint64_t adesc = ptx::make_kmajor_sw128_desc(sa0 + j * kDecABytes);
+                const uint64_t bdesc = ptx::make_kmajor_sw128_desc(sb0 + j * kBBlock);
+#pragma unroll
+                for (int k = 0; k < kDecBlockK / 16; ++k) {
+                  const uint32_t accum = (kb0 + j > 0 || k > 0) ? 1u : 0u;
+                  if constexpr (kPair) ptx::umma_f16_2sm(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, accum);
+                  else ptx::umma_f16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, accum);
+                }
+              }
+              if constexpr (kPair) ptx::umma_commit_2sm_mc(&empty_bar[stage], 3);
+              else ptx::umma_commit(&empty_bar[stage]);
+              if (last) {
+                if constexpr (kPair) ptx::umma_commit_2sm_mc(&tfull_bar[acc], 3);
+                else ptx::umma_commit(&tfull_bar[acc]);
+                if (n == n1 - 1) {                                   // the unit's last MMAs: the coefficient tile is free after them
+                  if constexpr (kPair) ptx::umma_commit_2sm_mc(aempty_bar, 3);
+                  else ptx::umma_commit(aempty_bar);
+                }
+              }
+            }
+            __syncwarp();
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          }
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1u;
+        }
+        aphase ^= 1u;
+      }
+    }
+  } else {
+    // ===================================================== epilogue warps
+    const int wq = warp & 3;                       // TMEM lane quarter
+    const int grp = (warp - 2) >> 2;               // column group: columns [96 grp, 96 grp + 96) of the tile
+    float* stage = reinterpret_cast<float*>(stage_out + (warp - 2) * kDecStageBytes);
+    float4* srow = reinterpret_cast<float4*>(stage + lane * kDecStagePitch);
+    const uint32_t tempty_cluster0 = kPair ? ptx::mapa_u32(&tempty_bar[0], 0) : 0u;
+    const uint32_t tempty_cluster1 = kPair ? ptx::mapa_u32(&tempty_bar[1], 0) : 0u;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    float R[12], Jw[12], cx = 0.f, cy = 0.f, cz = 0.f, sc = 1.f, tx = 0.f, ty = 0.f;
+    int m, n0, n1;
+    const int nv3 = p.nv * 3;
+    const int nv3s = p.debug == 4 ? ((nv3 + 7) & ~7) : nv3;      // debug 4: sector-aligned row pitch (timing experiment only)
+    const int pc = p.pc;
+    const float hs = 0.5f * p.image_size;
+    const unsigned rho_v = static_cast<unsigned>(nv3s) & 7u, rho_q = static_cast<unsigned>(p.nv * pc) & 7u;   // row pitch mod 8 floats
+    float vprev[8], qprev[8];                      // this row's last 8 floats of the previous pass (the carry), per output
+#pragma unroll
+    for (int j = 0; j < 8; ++j) vprev[j] = qprev[j] = 0.f;
+    for (int ui = 0; dec_unit_at(p, group, n_groups, ui, &m, &n0, &n1); ++ui) {
+      const int head0 = (kPair ? 2 * m + crank : m) * kDecBlockM + wq * 32;
+      {   // per-head transforms -> registers, once per unit (rows past the batch read the last valid record; never stored)
+        const int h = min(head0 + lane, p.rows - 1);
+        const float4* src = reinterpret_cast<const float4*>(p.xf + static_cast<size_t>(h) * kDecXfFloats);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          const float4 a = __ldg(&src[q]);           // joint 0 (rest)
+          const float4 b = __ldg(&src[6 + q]);       // joint 2 (jaw)
+          R[4 * q] = a.x; R[4 * q + 1] = a.y; R[4 * q + 2] = a.z; R[4 * q + 3] = a.w;
+          Jw[4 * q] = b.x; Jw[4 * q + 1] = b.y; Jw[4 * q + 2] = b.z; Jw[4 * q + 3] = b.w;
+        }
+        const float4 u = __ldg(&src[15]);
+        const float4 w = __ldg(&src[16]);
+        cx = u.x; cy = u.y; cz = u.z; sc = u.w; tx = w.x; ty = w.y;
+      }
+      const int rows_left = (p.debug == 4 ? p.rows - 32 : p.rows) - head0;   // rows of this warp inside the batch (<= 0: nothing to store)
+      const int head_store = p.debug == 1 ? (head0 & 127) : head0;
+      float* const v_base = p.verts3d ? p.verts3d + static_cast<size_t>(head_store) * nv3s : nullptr;
+      float* const q_base = p.proj ? p.proj + static_cast<size_t>(head_store) * p.nv * pc : nullptr;
+      // (w_rest, w_jaw) of the warp's 32 vertices of a tile: lane l holds floats 2*vertex+{0,1} of vertices l/2 and 16+l/2
+      int vb = n0 * (kDecN / 3) + grp * 32;
+      float wl0 = (vb * 2 + lane < p.nv * 2) ? __ldg(&p.w2[vb * 2 + lane]) : 0.f;
+      float wl1 = (vb * 2 + 32 + lane < p.nv * 2) ? __ldg(&p.w2[vb * 2 + 32 + lane]) : 0.f;
+      for (int n = n0; n < n1; ++n) {
+        const float wc0 = wl0, wc1 = wl1;
+        if (n + 1 < n1) {                            // next tile's table: the L2 latency hides behind this tile's work
+          const int vn = vb + kDecN / 3;
+          wl0 = (vn * 2 + lane < p.nv * 2) ? __ldg(&p.w2[vn * 2 + lane]) : 0.f;
+          wl1 = (vn * 2 + 32 + lane < p.nv * 2) ? __ldg(&p.w2[vn * 2 + 32 + lane]) : 0.f;
+        }
+        // sector phase of the tile's first float of row 0 of this warp (in floats, mod 8), for both outputs
+        const bool tile_full = rows_left >= 32 && (vb + 32) * 3 <= nv3;
+        const unsigned cb_v = v_base ? static_cast<unsigned>((reinterpret_cast<uintptr_t>(v_base + vb * 3) >> 2) & 7u) : 0u;
+        const unsigned cb_q = q_base ? static_cast<unsigned>((reinterpret_cast<uintptr_t>(q_base + vb * pc) >> 2) & 7u) : 0u;
+        ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+        ptx::tc_fence_after();
+        const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + static_cast<uint32_t>(acc * kDecN + grp * 96);
+        if (p.debug == 3) {
+          ptx::tc_fence_before();
+          if constexpr (kPair) ptx::mbar_arrive_cluster(acc ? tempty_cluster1 : tempty_cluster0);
+          else ptx::mbar_arrive(&tempty_bar[acc]);
+        }
+#pragma unroll 1
+        for (int q = 0; q < 4 && p.debug != 3; ++q) {          // 4 passes of 8 vertices (24 accumulator columns)
+          float xa[24];
+          ptx::tmem_ld_32x32b_x16_f(t_acc + q * 24, xa);
+          ptx::tmem_ld_32x32b_x8_f(t_acc + q * 24 + 16, xa + 16);
+          ptx::tmem_ld_wait();
+          if (q == 3) {                              // the warp's share of the accumulator has been read: hand TMEM back
+            ptx::tc_fence_before();
+            if constexpr (kPair) ptx::mbar_arrive_cluster(acc ? tempty_cluster1 : tempty_cluster0);
+            else ptx::mbar_arrive(&tempty_bar[acc]);
+          }
+          const float wl = (q & 2) ? wc1 : wc0;
+          const int lsel = (q & 1) * 16;
+          float x[24];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float px = xa[3 * i], py = xa[3 * i + 1], pz = xa[3 * i + 2];
+            const float wr = __shfl_sync(0xffffffffu, wl, lsel + 2 * i);
+            const float wj = __shfl_sync(0xffffffffu, wl, lsel + 2 * i + 1);
+            const float rx = fmaf(R[0], px, fmaf(R[1], py, fmaf(R[2], pz, R[3])));
+            const float ry = fmaf(R[4], px, fmaf(R[5], py, fmaf(R[6], pz, R[7])));
+            const float rz = fmaf(R[8], px, fmaf(R[9], py, fmaf(R[10], pz, R[11])));
+            const float jx = fmaf(Jw[0], px, fmaf(Jw[1], py, fmaf(Jw[2], pz, Jw[3])));
+            const float jy = fmaf(Jw[4], px, fmaf(Jw[5], py, fmaf(Jw[6], pz, Jw[7])));
+            const float jz = fmaf(Jw[8], px, fmaf(Jw[9], py, fmaf(Jw[10], pz, Jw[11])));
+            x[3 * i] = fmaf(wj, jx, fmaf(wr, rx, cx));
+            x[3 * i + 1] = fmaf(wj, jy, fmaf(wr, ry, cy));
+            x[3 * i + 2] = fmaf(wj, jz, fmaf(wr, rz, cz));
+          }
+          const int vfirst = vb + q * 8;
+          const int ncols = min(kDecPassCols, nv3 - vfirst * 3);        // valid floats of this pass's run (<= 0: past the mesh)
+          if (ncols <= 0 || rows_left <= 0 || p.debug == 2) continue;
+          if (v_base) {
+            // staged row = [8 carry floats of the previous pass | 24 new floats]
+            srow[0] = make_float4(vprev[0], vprev[1], vprev[2], vprev[3]);
+            srow[1] = make_float4(vprev[4], vprev[5], vprev[6], vprev[7]);
+#pragma unroll
+            for (int j = 0; j < 6; ++j) srow[2 + j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) vprev[j] = x[16 + j];
+            __syncwarp();
+            float* dst = v_base + vfirst * 3;
+            if (tile_full) dec_flush_aligned<24>(dst, static_cast<unsigned>(nv3s), stage, lane, (cb_v + 24u * q) & 7u, rho_v, q == 0, q == 3);
+            else dec_flush_edge<24>(dst, static_cast<unsigned>(nv3s), stage, lane, rows_left, ncols);
+            __syncwarp();
+          }
+          if (q_base) {
+            // head_mesh.py:39-43 (z translation is zero)
+            srow[0] = make_float4(qprev[0], qprev[1], qprev[2], qprev[3]);
+            srow[1] = make_float4(qprev[4], qprev[5], qprev[6], qprev[7]);
+            if (pc == 2) {
+              float qv[16];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                qv[2 * i] = ((x[3 * i] * sc + tx) + 1.0f) * hs;
+                qv[2 * i + 1] = ((x[3 * i + 1] * sc + ty) + 1.0f) * hs;
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) srow[2 + j] = make_float4(qv[4 * j], qv[4 * j + 1], qv[4 * j + 2], qv[4 * j + 3]);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) qprev[j] = qv[8 + j];
+            } else {
+              float qv[24];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                qv[3 * i] = ((x[3 * i] * sc + tx) + 1.0f) * hs;
+                qv[3 * i + 1] = ((x[3 * i + 1] * sc + ty) + 1.0f) * hs;
+                qv[3 * i + 2] = ((x[3 * i + 2] * sc + 0.0f) + 1.0f) * hs;
+              }
+#pragma unroll
+              for (int j = 0; j < 6; ++j) srow[2 + j] = make_float4(qv[4 * j], qv[4 * j + 1], qv[4 * j + 2], qv[4 * j + 3]);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) qprev[j] = qv[16 + j];
+            }
+            __syncwarp();
+            const unsigned pitch = static_cast<unsigned>(p.nv * pc);
+            float* dst = q_base + vfirst * pc;
+            const int nval = (ncols / 3) * pc;
+            if (pc == 2) {
+              if (tile_full) dec_flush_aligned<16>(dst, pitch, stage, lane, (cb_q + 16u * q) & 7u, rho_q, q == 0, q == 3);
+              else dec_flush_edge<16>(dst, pitch, stage, lane, rows_left, nval);
+            } else {
+              if (tile_full) dec_flush_aligned<24>(dst, pitch, stage, lane, (cb_q + 24u * q) & 7u, rho_q, q == 0, q == 3);
+              else dec_flush_edge<24>(dst, pitch, stage, lane, rows_left, nval);
+            }
+            __syncwarp();
+          }
+        }
+        vb += kDecN / 3;
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if constexpr (kPair) ptx::cluster_sync_all();      // nobody leaves while the peer may still signal my barriers
+  if (warp == 0) {
+    ptx::tc_fence_after();
+    if constexpr (kPair) ptx::tmem_dealloc_2sm(tmem_base, 512);
+    else ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace dad3d

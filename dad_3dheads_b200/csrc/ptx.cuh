@@ -52,6 +52,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// non-blocking probe of the phase (never suspends the thread)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded spin: a protocol bug shows up as a trapped kernel (cudaErrorLaunchFailure) instead of a hung GPU box.
 #ifndef DAD3D_WATCHDOG_SPINS
 #define DAD3D_WATCHDOG_SPINS (1u << 22)
@@ -61,6 +75,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > DAD3D_WATCHDOG_SPINS) {
       printf("dad3d: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
+             smem_u32(bar), parity);
+      __trap();
+    }
+  }
+}
+
+// polling wait (test_wait in a tight loop): lowest wake-up latency, for the single-purpose producer / MMA-issuer warps
+__device__ __forceinline__ void mbar_wait_poll(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_test_wait(bar, parity)) {
+    if (++spins > (DAD3D_WATCHDOG_SPINS << 4)) {
+      printf("dad3d: mbarrier poll timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
              smem_u32(bar), parity);
       __trap();
     }

@@ -146,8 +146,13 @@ class FlameDecoder:
 
     def decode(self, params: Tensor, *, want_vertices: bool = True, want_projected: bool = False, to_2d: bool = True,
                zero_rot: bool = False, zero_jaw: bool = False, image_size: float = 256.0, fast: bool = False,
-               simt: bool = False, unfused: bool = False, cluster: bool = False):
-        """params: [B, num_params] fp32 CUDA tensor on this decoder's device.  Returns (vertices3d|None, projected|None)."""
+               simt: bool = False, unfused: bool = False, cluster: bool = False, hilo: bool = False, pair: bool = False):
+        """params: [B, num_params] fp32 CUDA tensor on this decoder's device.  Returns (vertices3d|None, projected|None).
+
+        Default = the dedicated one-product decode kernel (fp16 operands, fp32 accumulate; vertices relL2 ~1.5e-5 vs fp64,
+        inside the 1e-4 contract).  ``hilo=True`` = fp16 hi/lo split operands, 3 tensor-core products (relL2 ~2e-7).
+        ``fast`` is the old name of today's default and has no effect; ``pair`` / ``cluster`` / ``unfused`` / ``simt`` are
+        A/B and verification switches (include/dad3d.h)."""
         assert params.is_cuda and params.dtype == torch.float32 and params.ndim == 2
         assert params.shape[1] == self.num_params, (params.shape, self.num_params)
         params = params.contiguous()
@@ -159,7 +164,8 @@ class FlameDecoder:
             return v3, pj
         flags = ((_lib.DAD3D_ZERO_ROT if zero_rot else 0) | (_lib.DAD3D_ZERO_JAW if zero_jaw else 0) |
                  (_lib.DAD3D_BLEND_FAST if fast else 0) | (_lib.DAD3D_BLEND_SIMT if simt else 0) |
-                 (_lib.DAD3D_DECODE_UNFUSED if unfused else 0) | (_lib.DAD3D_DECODE_CLUSTER if cluster else 0))
+                 (_lib.DAD3D_DECODE_UNFUSED if unfused else 0) | (_lib.DAD3D_DECODE_CLUSTER if cluster else 0) |
+                 (_lib.DAD3D_BLEND_HILO if (hilo or cluster) else 0) | (_lib.DAD3D_DECODE_PAIR if pair else 0))
         nbytes = int(self.lib.dad3d_flame_workspace_bytes(self._h, B))
         ws = self._ws.get(params.device, nbytes)
         stream = torch.cuda.current_stream(params.device).cuda_stream
@@ -223,6 +229,7 @@ class FLAMELayer(nn.Module):
         self.batch_size = batch_size
         self.dtype = torch.float32
         self._cuda_id = cuda_id
+        self.strict = True      # the reference-facing ``forward`` (per-image calls) uses the 3-product hi/lo blend (2e-7)
         self._decoders: Dict[int, FlameDecoder] = {}
         # attributes other reference code reads (inference/pncc_estimator.py:72,90, demo_utils.py:108-111)
         self.flame_model = SimpleNamespace(v_template=st["v_template"], f=st.get("faces"))
@@ -253,5 +260,5 @@ class FLAMELayer(nn.Module):
         src_device = packed.device
         dec = self.decoder(src_device)
         v3, _ = dec.decode(packed.to(dec.device, non_blocking=True), want_vertices=True, want_projected=False,
-                           zero_rot=zero_rot, zero_jaw=zero_jaw)
+                           zero_rot=zero_rot, zero_jaw=zero_jaw, hilo=self.strict)
         return v3 if src_device.type == "cuda" else v3.to(src_device)

@@ -182,7 +182,7 @@ class FaceMeshPredictor:
             landmarks = self.readjust_landmarks_to_the_input_image(landmarks, paddings, scale)
             pred_3dmm = self.readjust_3dmm_to_the_input_image(pred_3dmm, paddings, scale)
             # the reference decodes twice (predictor.py:136-137); one GPU pass yields both outputs
-            v3, proj = self.head_mesh.decode(pred_3dmm, to_2d=True)
+            v3, proj = self.head_mesh.decode(pred_3dmm, to_2d=True, hilo=True)     # per-image path: strict blend
             ti = self.find_3dmm_idx("translation", self.flame_constants)
             pred_3dmm[:, ti + 2] = 0.0                       # side effect of reprojected_vertices (head_mesh.py:41)
             return {"points": landmarks, "projected_vertices": proj, "3d_vertices": v3[0].squeeze(),
@@ -251,7 +251,7 @@ class FaceMeshPredictor:
         return self._lm_index[subset]
 
     def predict_batch(self, images: Tensor, landmark_subset: Optional[str] = "445", to_2d: bool = True,
-                      fast_decode: bool = False) -> Dict[str, Tensor]:
+                      fast_decode: bool = True) -> Dict[str, Tensor]:
         """images: [B,3,256,256] fp32 already letter-boxed + normalised, or raw RGB as the reference's ``__call__`` takes it:
         one [B,H,W,3] uint8 tensor / a list of HxWx3 uint8 images (letter-boxed + normalised on the GPU, bit-identical to
         the reference's albumentations pipeline); host or device.  All outputs stay on the GPU:
@@ -262,7 +262,7 @@ class FaceMeshPredictor:
         else:
             x = images.to(self.device, torch.float32, non_blocking=True)
         params, lms, _ = self.model.forward_raw(x, want_heatmap=False)
-        v3, proj = self.head_mesh.decode(params, to_2d=to_2d, fast=fast_decode)
+        v3, proj = self.head_mesh.decode(params, to_2d=to_2d, hilo=not fast_decode)
         out = {"3dmm_params": params, "points": lms * float(self._img_size), "3d_vertices": v3,
                "projected_vertices": proj}
         if landmark_subset is not None:
@@ -290,7 +290,7 @@ class FaceMeshPredictor:
         return graph, out, self._ws_generation()
 
     def predict_batch_graphed(self, images: Tensor, landmark_subset: Optional[str] = "445", to_2d: bool = True,
-                              fast_decode: bool = False) -> Dict[str, Tensor]:
+                              fast_decode: bool = True) -> Dict[str, Tensor]:
         """:meth:`predict_batch` replayed from a CUDA graph (one graph per input shape / dtype / option set): the ~110 kernel
         launches of a step become one graph launch, which removes the launch gaps between the many sub-20 us layers.
         ``images`` is copied into the graph's static input buffer (host or device source); the returned tensors are the
@@ -333,7 +333,7 @@ class BatchStream:
     """
 
     def __init__(self, predictor: FaceMeshPredictor, shape, dtype=torch.uint8, landmark_subset: Optional[str] = "445",
-                 to_2d: bool = True, fast_decode: bool = False, depth: int = 2,
+                 to_2d: bool = True, fast_decode: bool = True, depth: int = 2,
                  keys=("3dmm_params", "points", "3d_vertices", "landmarks_445"), host_results: bool = True,
                  group=None, gather_keys=("3dmm_params", "3d_vertices", "landmarks_445")):
         self.pred = predictor

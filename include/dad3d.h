@@ -47,8 +47,13 @@ typedef struct dad3d_flame_layout {
 /* decode flags */
 #define DAD3D_ZERO_ROT 1        /* FLAMELayer.forward(zero_rot=True)   flame.py:225 */
 #define DAD3D_ZERO_JAW 2        /* FLAMELayer.forward(zero_jaw=True)   flame.py:206 */
-#define DAD3D_BLEND_FAST 4      /* blend-shape product in ONE fp16 tensor-core pass (11-bit operands, like TF32);
-                                   default is the 3-product hi/lo split (fp32-class accuracy) */
+#define DAD3D_BLEND_FAST 4      /* (old name of today's default; accepted, no effect) */
+#define DAD3D_BLEND_HILO 64     /* blend-shape product with fp16 hi/lo split operands (3 tensor-core products, 22-bit, vertices
+                                   relL2 2e-7 vs fp64) through the generic tile engine.  DEFAULT (flag absent): ONE fp16 product
+                                   (11-bit operand mantissa like TF32, template exact to 22 bits; vertices relL2 1.5e-5, inside
+                                   the 1e-4 contract) in the dedicated A-stationary decode kernel (csrc/flame_decode.cuh) */
+#define DAD3D_DECODE_PAIR 128   /* A/B aid: run the dedicated decode kernel as CTA pairs (cta_group::2) when the batch has at
+                                   least two row tiles per SM (also: environment DAD3D_DECODE_PAIR=1) */
 #define DAD3D_BLEND_SIMT 8      /* verification aid: blend-shape product on CUDA cores in fp32 (slow) */
 #define DAD3D_DECODE_UNFUSED 16 /* A/B aid: tensor-core blend product to a v_posed scratch + separate skinning kernel
                                    (default: skinning / rotation / projection fused into the GEMM epilogue) */

@@ -1,9 +1,10 @@
 """-m gpu: the CUDA FLAME decoder (through the C ABI) against the CPU oracle on identical seeded inputs.
 
-Tolerances (fp32 path, BASELINE.json north_star: 1e-4 relative):
-  precise mode (default, fp16 hi/lo 3-product blend):  norm-wise relL2 < 2e-6, max abs error < 2e-6 * max|ref|  (i.e. at
-      the oracle's own fp32-vs-fp64 noise level), far inside the 1e-4 contract
-  fast mode (one fp16 pass, TF32-class operands):       norm-wise relL2 < 1e-4 (stated with every number that uses it)
+Tolerances (BASELINE.json north_star: 1e-4 relative, vertex L2 < 1e-4):
+  default (dedicated decode kernel, ONE fp16 tensor-core product, TF32-class operands, template exact to 22 bits):
+      norm-wise relL2 < 5e-5 (measured 1.5e-5), element-wise |err| <= 1e-4 |ref| + 1e-5 m, per-vertex L2 < 1e-4 m
+  hilo=True (fp16 hi/lo 3-product blend through the tile engine; what the reference-facing per-image methods use):
+      norm-wise relL2 < 2e-6, max abs error < 4e-6 * max|ref|  (the oracle's own fp32-vs-fp64 noise level)
 """
 import numpy as np
 import pytest
@@ -45,14 +46,33 @@ def test_simt_blend_matches_oracle(head_mesh, oracle64, cuda_device):
 
 
 @pytest.mark.parametrize("B", [1, 2, 3, 4, 64, 127, 128, 129, 512])
-def test_decode_matches_oracle(head_mesh, oracle64, cuda_device, B):
+@pytest.mark.parametrize("hilo", [False, True])
+def test_decode_matches_oracle(head_mesh, oracle64, cuda_device, B, hilo):
     p = sample_params(B, seed=100 + B)
-    v3, pj = head_mesh.decode(p.to(cuda_device))
+    v3, pj = head_mesh.decode(p.to(cuda_device), hilo=hilo)
     v_ref = oracle64.vertices_3d(p)
     p_ref = oracle64.reprojected_vertices(p)
     assert v3.shape == (B, 5023, 3) and pj.shape == (B, 5023, 2)
-    assert _rel(v3, v_ref) < 2e-6 and _maxrel(v3, v_ref) < 4e-6, (_rel(v3, v_ref), _maxrel(v3, v_ref))
-    assert _rel(pj, p_ref) < 2e-6 and _maxrel(pj, p_ref) < 4e-6
+    tol, mtol = (2e-6, 4e-6) if hilo else (5e-5, 2e-4)
+    assert _rel(v3, v_ref) < tol and _maxrel(v3, v_ref) < mtol, (_rel(v3, v_ref), _maxrel(v3, v_ref))
+    assert _rel(pj, p_ref) < tol and _maxrel(pj, p_ref) < mtol
+    assert (v3.double().cpu() - v_ref).norm(dim=-1).max().item() < 1e-4          # north_star: vertex L2 < 1e-4
+
+
+@pytest.mark.parametrize("B", [1, 77, 300])
+def test_decode_3d_projection_and_single_outputs(head_mesh, oracle64, cuda_device, B):
+    """to_2d=False (3-component projection) and the one-output variants of the default kernel."""
+    dec = head_mesh.flame.decoder(cuda_device)
+    p = sample_params(B, seed=200 + B)
+    d = p.to(cuda_device)
+    v3, pj3 = dec.decode(d, want_vertices=True, want_projected=True, to_2d=False)
+    assert _rel(pj3, oracle64.reprojected_vertices(p, to_2d=False)) < 5e-5
+    only_v = dec.decode(d, want_vertices=True, want_projected=False)
+    only_p = dec.decode(d, want_vertices=False, want_projected=True, to_2d=False)
+    assert only_v[1] is None and only_p[0] is None
+    assert torch.equal(only_v[0], v3) and torch.equal(only_p[1], pj3)
+    _, pj2 = dec.decode(d, want_vertices=False, want_projected=True, to_2d=True)
+    assert torch.equal(pj2, pj3[..., :2])
 
 
 def test_decode_matches_fp32_oracle_within_contract(head_mesh, flame_static, cuda_device):
@@ -60,15 +80,19 @@ def test_decode_matches_fp32_oracle_within_contract(head_mesh, flame_static, cud
     p = sample_params(16, seed=5)
     o32 = FlameOracle(flame_static)
     v_ref = o32.vertices_3d(p)
-    v3, _ = head_mesh.decode(p.to(cuda_device))
+    v3, _ = head_mesh.decode(p.to(cuda_device), hilo=True)
     err = (v3.cpu() - v_ref).abs()
     assert (err <= 1e-4 * v_ref.abs() + 1e-6).all()        # rtol 1e-4, atol 1 micrometre for coordinates near 0
     assert _rel(v3, v_ref) < 1e-5
+    v3, _ = head_mesh.decode(p.to(cuda_device))            # default one-product kernel: atol 10 micrometres
+    err = (v3.cpu() - v_ref).abs()
+    assert (err <= 1e-4 * v_ref.abs() + 1e-5).all(), (err - 1e-4 * v_ref.abs()).max()
+    assert _rel(v3, v_ref) < 5e-5
 
 
 def test_fast_mode_within_stated_tolerance(head_mesh, oracle64, cuda_device):
     p = sample_params(32, seed=6)
-    v3, pj = head_mesh.decode(p.to(cuda_device), fast=True)
+    v3, pj = head_mesh.decode(p.to(cuda_device))
     assert _rel(v3, oracle64.vertices_3d(p)) < 1e-4
     assert _rel(pj, oracle64.reprojected_vertices(p)) < 1e-4
 
@@ -150,8 +174,14 @@ def test_chunk_boundary_and_batch_independence(head_mesh, cuda_device):
     assert torch.isfinite(v3).all()
     # opt-in variant: big passes as 2x2 thread-block clusters with TMA multicast of both operands -- same arithmetic
     n = props.multi_processor_count * 128 + 77
-    va, pa = dec.decode(p[:n], want_vertices=True, want_projected=True)
+    va, pa = dec.decode(p[:n], want_vertices=True, want_projected=True, hilo=True)
     vb, pb = dec.decode(p[:n], want_vertices=True, want_projected=True, cluster=True)
+    assert torch.equal(va, vb) and torch.equal(pa, pb)
+    del va, pa, vb, pb
+    # opt-in variant of the default kernel: CTA pairs (cta_group::2) for batches with >= 2 row tiles per SM -- same arithmetic
+    n = props.multi_processor_count * 128 * 2 + 77
+    va, pa = dec.decode(p[:n], want_vertices=True, want_projected=True)
+    vb, pb = dec.decode(p[:n], want_vertices=True, want_projected=True, pair=True)
     assert torch.equal(va, vb) and torch.equal(pa, pb)
 
 
@@ -160,15 +190,15 @@ def test_fused_equals_unfused(head_mesh, oracle64, cuda_device):
     dec = head_mesh.flame.decoder(cuda_device)
     p = sample_params(300, seed=21)
     for to_2d in (True, False):
-        a = dec.decode(p.to(cuda_device), want_vertices=True, want_projected=True, to_2d=to_2d)
+        a = dec.decode(p.to(cuda_device), want_vertices=True, want_projected=True, to_2d=to_2d, hilo=True)
         b = dec.decode(p.to(cuda_device), want_vertices=True, want_projected=True, to_2d=to_2d, unfused=True)
         assert (a[0] - b[0]).abs().max().item() < 1e-7 and (a[1] - b[1]).abs().max().item() < 1e-4
         assert _rel(b[0], oracle64.vertices_3d(p)) < 2e-6
         assert _rel(a[1], oracle64.reprojected_vertices(p, to_2d=to_2d)) < 2e-6
-    only_v = dec.decode(p.to(cuda_device), want_vertices=True, want_projected=False)
-    only_p = dec.decode(p.to(cuda_device), want_vertices=False, want_projected=True)
+    only_v = dec.decode(p.to(cuda_device), want_vertices=True, want_projected=False, hilo=True)
+    only_p = dec.decode(p.to(cuda_device), want_vertices=False, want_projected=True, hilo=True)
     assert only_v[1] is None and only_p[0] is None
-    assert torch.equal(only_v[0], a[0]) and torch.equal(only_p[1], dec.decode(p.to(cuda_device), want_projected=True)[1])
+    assert torch.equal(only_v[0], a[0]) and torch.equal(only_p[1], dec.decode(p.to(cuda_device), want_projected=True, hilo=True)[1])
 
 
 def test_blend_linearity_property(head_mesh, cuda_device):
@@ -180,9 +210,12 @@ def test_blend_linearity_property(head_mesh, cuda_device):
     b[:, :400] = torch.randn(256, 400, generator=g)
     z = torch.zeros(256, 413)
     dec = head_mesh.flame.decoder(cuda_device)
-    f = lambda x: dec.decode(x.to(cuda_device), zero_rot=True)[0].double()
+    f = lambda x: dec.decode(x.to(cuda_device), zero_rot=True, hilo=True)[0].double()
     r = f(a + b) - f(a) - f(b) + f(z)
     assert r.abs().max().item() < 5e-7
+    f = lambda x: dec.decode(x.to(cuda_device), zero_rot=True)[0].double()       # default kernel: betas are rounded to fp16
+    r = f(a + b) - f(a) - f(b) + f(z)
+    assert r.abs().max().item() < 3e-5
 
 
 def test_landmark_gathers(head_mesh, flame_static, cuda_device):
@@ -215,11 +248,12 @@ def test_reference_fixture(head_mesh, cuda_device, B):
     import os
     z = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_flame.npz"))
     p = torch.from_numpy(z[f"params_b{B}"])
-    v3, pj = head_mesh.decode(p.to(cuda_device), to_2d=False)
-    assert _rel(v3, torch.from_numpy(z[f"vertices3d_f64_b{B}"])) < 2e-6
-    assert _rel(pj, torch.from_numpy(z[f"projected3_f64_b{B}"])) < 2e-6
-    l2 = (v3.double().cpu() - torch.from_numpy(z[f"vertices3d_f64_b{B}"])).norm(dim=-1).max().item()
-    assert l2 < 1e-6, l2                                        # per-vertex L2 in metres (target < 1e-4)
+    for hilo, tol, l2tol in ((True, 2e-6, 1e-6), (False, 5e-5, 1e-4)):     # strict hi/lo blend; default one-product kernel
+        v3, pj = head_mesh.decode(p.to(cuda_device), to_2d=False, hilo=hilo)
+        assert _rel(v3, torch.from_numpy(z[f"vertices3d_f64_b{B}"])) < tol
+        assert _rel(pj, torch.from_numpy(z[f"projected3_f64_b{B}"])) < tol
+        l2 = (v3.double().cpu() - torch.from_numpy(z[f"vertices3d_f64_b{B}"])).norm(dim=-1).max().item()
+        assert l2 < l2tol, l2                                   # per-vertex L2 in metres (north_star target < 1e-4)
     vz = head_mesh.vertices_3d(p.to(cuda_device), zero_rotation=True)
     assert _rel(vz, torch.from_numpy(z[f"vertices3d_zero_rot_f32_b{B}"])) < 2e-6
     q = p.clone()
