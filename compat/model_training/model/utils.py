@@ -7,6 +7,41 @@ import torch.nn.functional as F
 from dad_3dheads_b200.predictor import calculate_paddings  # noqa: F401
 
 
+def get_flame_model(flame_path=None):
+    """model/utils.py:84-89: the FLAME constants as an attribute bag (``v_template, shapedirs, posedirs, J_regressor,
+    kintree_table, weights, f``); a ``flame.pkl`` path is read with the package's restricted unpickler."""
+    from types import SimpleNamespace
+
+    import numpy as np
+
+    from dad_3dheads_b200.flame import load_flame_static
+    st = load_flame_static(flame_path)
+    nv = st["v_template"].shape[0]
+    kintree = np.stack([np.where(st["parents"] < 0, 4294967295, st["parents"]).astype(np.int64), np.arange(st["parents"].size)])
+    return SimpleNamespace(v_template=st["v_template"], shapedirs=st["shapedirs"],
+                           posedirs=st["posedirs"].T.reshape(nv, 3, -1), J_regressor=st["J_regressor"],
+                           kintree_table=kintree, weights=st["lbs_weights"], f=st["faces"])
+
+
+def get_flame_indices(name: str = "head_indices"):
+    """model/utils.py:80-81: static/<name>.npy; served from the packed asset (``indices_2d``, ``flame_indices_*``)."""
+    from dad_3dheads_b200.flame import load_flame_static
+    st = load_flame_static()
+    for key in (name, "flame_indices_" + name, "flame_indices_" + name.replace("_indices", "")):
+        if key in st:
+            return st[key]
+    raise FileNotFoundError(f"static/{name}.npy is not part of the packed FLAME asset")
+
+
+def normalize_to_cube(v: torch.Tensor) -> torch.Tensor:
+    """model/utils.py:55-68: vertices [B,N,3] (or [N,3]) -> the unit cube [-1,1]^3."""
+    if v.ndim == 2:
+        v = v[None]
+    v = v - v.min(1, True)[0]
+    v = v - 0.5 * v.max(1, True)[0]
+    return v / v.max(-1, True)[0].max(-2, True)[0]
+
+
 def to_device(x, cuda_id: int = 0):
     return x.cuda(cuda_id) if torch.cuda.is_available() else x
 

@@ -79,8 +79,10 @@ class FlameParams:
 
 
 def load_flame_static(path: Optional[str] = None) -> Dict[str, np.ndarray]:
-    with np.load(path or _ASSET) as z:
-        return {k: z[k] for k in z.files}
+    """The FLAME constants: the packed ``assets/flame_static.npz`` by default, or -- like the reference's
+    ``get_flame_model(flame_path)`` (model/utils.py:84-89) -- a ``flame.pkl`` given by path (flame_assets.py)."""
+    from .flame_assets import load_static
+    return load_static(path, _ASSET)
 
 
 class _Workspace:

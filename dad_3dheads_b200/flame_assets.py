@@ -1,0 +1,117 @@
+"""Readers of the reference's static FLAME assets (model_training/model/utils.py:80-89 ``get_flame_indices`` /
+``get_flame_model``; flame.py:124-180 says how ``FLAMELayer.__init__`` consumes the pickle).
+
+``flame.pkl`` is a python-2 era pickle that references ``chumpy.ch.Ch`` and ``scipy.sparse.csc.csc_matrix``; chumpy is not a
+dependency of this package, so a restricted unpickler substitutes a stub for it (payload attribute ``x``) and refuses every
+class outside numpy / scipy.sparse / builtins.  ``load_flame_pickle`` returns the same fp32 arrays the packed
+``assets/flame_static.npz`` holds (tests/test_oracle_pinned.py checks the two bit for bit against the reference's own
+FLAMELayer buffers), so ``FLAMELayer(consts, flame_path=".../flame.pkl")`` works at run time exactly like the reference's.
+"""
+from __future__ import annotations
+
+import os
+import pickle
+from typing import Dict, Optional
+
+import numpy as np
+
+
+class _ChStub:
+    """Stand-in for chumpy.ch.Ch: keeps whatever state the pickle gives it; the array payload is ``x``."""
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+
+
+class _RestrictedUnpickler(pickle.Unpickler):
+    _ALLOWED_PREFIX = ("numpy", "scipy.sparse", "collections", "builtins", "copyreg")
+
+    def find_class(self, module, name):
+        if module.startswith("chumpy"):
+            return _ChStub
+        if module in ("scipy.sparse.csc", "scipy.sparse._csc") and name == "csc_matrix":
+            import scipy.sparse
+            return scipy.sparse.csc_matrix
+        module = {"__builtin__": "builtins", "copy_reg": "copyreg"}.get(module, module)
+        if not module.startswith(self._ALLOWED_PREFIX):
+            raise pickle.UnpicklingError(f"refusing to unpickle {module}.{name}")
+        return super().find_class(module, name)
+
+
+def _np(x, dtype=None) -> np.ndarray:
+    if isinstance(x, _ChStub):
+        x = x.x
+    if hasattr(x, "todense"):
+        x = np.asarray(x.todense())
+    x = np.asarray(x)
+    return x.astype(dtype) if dtype is not None else x
+
+
+def load_pickle(path: str):
+    with open(path, "rb") as f:
+        return _RestrictedUnpickler(f, encoding="latin1").load()
+
+
+def load_flame_pickle(path: str) -> Dict[str, np.ndarray]:
+    """flame.pkl -> {v_template [V,3], shapedirs [V,3,400], posedirs [36,3V], J_regressor [5,V], parents [5], lbs_weights
+    [V,5], faces [F,3]} in fp32 / int32, with the reference's reshapes (flame.py:171-178)."""
+    fl = load_pickle(path)
+    posedirs_raw = _np(fl["posedirs"], np.float64)                       # [V,3,36]
+    parents = _np(fl["kintree_table"]).astype(np.int64)[0].copy()
+    parents[0] = -1                                                       # flame.py:176-178
+    out = {
+        "v_template": _np(fl["v_template"], np.float32),
+        "shapedirs": _np(fl["shapedirs"], np.float32),
+        "posedirs": np.reshape(posedirs_raw, [-1, posedirs_raw.shape[-1]]).T.astype(np.float32),   # flame.py:171-173
+        "J_regressor": _np(fl["J_regressor"], np.float32),
+        "parents": parents.astype(np.int32),
+        "lbs_weights": _np(fl["weights"], np.float32),
+        "faces": _np(fl["f"]).astype(np.int32),
+    }
+    here = os.path.dirname(os.path.abspath(path))
+    idx = os.path.join(here, "indices_2d.npy")                           # flame.py:132 (get_flame_indices("indices_2d"))
+    if os.path.isfile(idx):
+        out["indices_2d"] = np.load(idx).astype(np.int32)
+    return out
+
+
+def load_indices_from_npy(filepath: str):
+    """model_training/utils.py:99-105: an .npy holding an ordered dict of index lists -> one flat list."""
+    data = np.load(filepath, allow_pickle=True)[()]
+    lst = []
+    for value in data.values():
+        lst += list(value)
+    return lst
+
+
+def get_list_of_npy_files(config: Dict) -> list:
+    """model_training/utils.py:81-96: the .npy files of a key-point subset folder, minus ``2d_keys_exclude`` (default cheeks)."""
+    subset_path = str(config.get("2d_subset_path"))
+    subset = config.get("2d_keys", "all")
+    exclude = config.get("2d_keys_exclude", "cheeks")
+    files = os.listdir(subset_path)
+    if isinstance(subset, str) and subset == "all":
+        subset = [x.split(".")[0] for x in files]
+        if exclude is not None:
+            if isinstance(exclude, str):
+                exclude = [exclude]
+            for feature in exclude:
+                if feature in subset:
+                    subset.remove(feature)
+        subset = [os.path.join(subset_path, x + ".npy") for x in subset]
+    return subset
+
+
+def load_static(path: Optional[str], default_npz: str) -> Dict[str, np.ndarray]:
+    """``path`` None -> the packed npz; ``*.pkl`` -> the reference's pickle (landmark tables etc. are then taken from the packed
+    npz, which holds everything else the path needs); anything else -> an npz in the packed format."""
+    def npz(p):
+        with np.load(p) as z:
+            return {k: z[k] for k in z.files}
+    if path is None:
+        return npz(default_npz)
+    if str(path).endswith(".pkl"):
+        st = npz(default_npz) if os.path.isfile(default_npz) else {}
+        st.update(load_flame_pickle(path))
+        return st
+    return npz(path)

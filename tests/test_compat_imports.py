@@ -25,3 +25,33 @@ def test_reference_module_paths_resolve():
         "print('ok')\n" % (ROOT, os.path.join(ROOT, "compat")))
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_reference_demo_modules_import_over_compat():
+    """Every symbol the reference's demo.py / demo_utils.py import (demo.py:1-20, demo_utils.py:1-12) resolves with compat/
+    first on sys.path: the reference's own demo_utils.py is imported UNCHANGED (source tree here, bytecode twin on the GPU box);
+    only third-party packages the image lacks (fire, pytorch_toolbelt) come from oracle/ref_shims."""
+    import pytest
+    from oracle import ref_harness as R
+    if not R.available():
+        pytest.skip("reference tree not available")
+    code = (
+        "import sys; sys.path[:0] = [%r, %r, %r, %r]\n"
+        "import demo_utils\n"
+        "from demo_utils import (draw_landmarks, draw_3d_landmarks, draw_mesh, draw_pose, get_uv_texture, get_pncc, get_mesh,\n"
+        "                        get_flame_params, get_output_path, MeshSaver, ImageSaver, JsonSaver)\n"
+        "from predictor import FaceMeshPredictor\n"
+        "from fire import Fire\n"
+        "from pytorch_toolbelt.utils import read_rgb_image\n"
+        "from model_training.utils import load_indices_from_npy, get_list_of_npy_files\n"
+        "from model_training.model.utils import get_flame_model, get_flame_indices, normalize_to_cube\n"
+        "import model_training.head_mesh, inference.uv_texture, inference.pncc_estimator\n"
+        "assert 'dad_3dheads_b200' in sys.modules['predictor'].FaceMeshPredictor.__module__\n"
+        "assert get_flame_model().v_template.shape == (5023, 3) and get_flame_indices('indices_2d').shape == (191,)\n"
+        "import torch\n"
+        "p = torch.zeros(1, 413); p[0, 403] = 1; p[0, 407] = 1\n"
+        "d = get_flame_params({'3dmm_params': p})\n"
+        "assert list(d) == ['shape', 'expression', 'rotation', 'translation', 'scale', 'jaw', 'eyeballs', 'neck']\n"
+        "print('ok')\n" % (os.path.join(ROOT, "compat"), ROOT, os.path.join(ROOT, "oracle", "ref_shims"), R.root()))
+    out = subprocess.run([sys.executable, "-W", "ignore", "-c", code], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]

@@ -196,3 +196,15 @@ def test_reference_state_dict_names_are_the_synthetic_ones():
     m = R.flame_regression(sd)
     own = {k for k in m.state_dict() if not k.endswith("num_batches_tracked")}
     assert own == set(sd)
+
+
+@needs_ref
+def test_runtime_flame_pickle_loader_matches_packed_asset():
+    """``FLAMELayer(consts, flame_path=".../flame.pkl")`` (flame.py:124-131 / model/utils.py:84-89): the package's restricted
+    unpickler reads the reference's own pickle at run time and yields exactly the packed asset's arrays."""
+    from dad_3dheads_b200.flame import load_flame_static
+    pkl = os.path.join(R.root(), "model_training", "model", "static", "flame.pkl")
+    a, b = load_flame_static(), load_flame_static(pkl)
+    for k in ("v_template", "shapedirs", "posedirs", "J_regressor", "parents", "lbs_weights", "faces", "indices_2d"):
+        assert a[k].dtype == b[k].dtype and np.array_equal(a[k], b[k]), k
+    assert "keypoints_445" in b            # landmark tables still come from the packed asset
