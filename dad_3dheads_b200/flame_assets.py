@@ -108,10 +108,17 @@ def load_static(path: Optional[str], default_npz: str) -> Dict[str, np.ndarray]:
     def npz(p):
         with np.load(p) as z:
             return {k: z[k] for k in z.files}
+    def extras(st):
+        # static/head_indices.npy (benchmark evaluator: get_flame_indices() default, dad_3dheads_benchmark/utils.py:310-311)
+        # lives beside the packed npz as a small file of its own
+        hp = os.path.join(os.path.dirname(default_npz), "head_indices.npy")
+        if "head_indices" not in st and os.path.isfile(hp):
+            st["head_indices"] = np.load(hp)
+        return st
     if path is None:
-        return npz(default_npz)
+        return extras(npz(default_npz))
     if str(path).endswith(".pkl"):
-        st = npz(default_npz) if os.path.isfile(default_npz) else {}
+        st = extras(npz(default_npz)) if os.path.isfile(default_npz) else {}
         st.update(load_flame_pickle(path))
         return st
-    return npz(path)
+    return extras(npz(path))

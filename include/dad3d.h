@@ -180,6 +180,23 @@ DAD3D_API int dad3d_encoder_set_debug(dad3d_encoder* enc, int32_t keep_all);
 DAD3D_API int dad3d_encoder_read_activation(dad3d_encoder* enc, const char* name, float* out_d, size_t capacity_floats,
                                             int32_t* dims4, dad3d_stream stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Benchmark evaluator hot spots (dad_3dheads_benchmark/benchmark.py, dad_3dheads_benchmark/utils.py),
+ * batched over B heads, device pointers, asynchronous on `stream`.
+ *   dad3d_eval_chamfer : out[b] = mean_i min_j |a[b,i] - b[b,j]|^2 -- the term the evaluator asks kaolin for
+ *                        (utils.py:139: chamfer_distance(gt_face, aligned_pred, 1.0, 0.0)); a [B,na,3], b [B,nb,3].
+ *   dad3d_eval_zn      : Z_n ordinal depth accuracy exactly as DADEvaluator.calc_zn computes it (benchmark.py:110-138):
+ *                        distances gt->gt (torch.cdist formula), COLUMN-wise argsort, columns 1..top_k of the index matrix,
+ *                        mean agreement of the z-order of (i, index[i][j]) between gt and pred.  pred, gt [B,K,3], K <= 4096.
+ *   dad3d_eval_align   : out = scale[b] * (verts[b] @ rot[b]) + trans[b] for every vertex (utils.py:178-197; rot [B,3,3]
+ *                        row-major, the procrustes tform of the 7 landmark pairs). */
+DAD3D_API int dad3d_eval_chamfer(const float* a_d, int32_t na, const float* b_d, int32_t nb, int32_t B, float* out_d,
+                                 dad3d_stream stream);
+DAD3D_API int dad3d_eval_zn(const float* pred_d, const float* gt_d, int32_t K, int32_t B, int32_t top_k, float* out_d,
+                            dad3d_stream stream);
+DAD3D_API int dad3d_eval_align(const float* verts_d, int32_t nv, int32_t B, const float* scale_d, const float* rot_d,
+                               const float* trans_d, float* out_d, dad3d_stream stream);
+
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 DAD3D_API unsigned long long dad3d_launch_count(void);
 

@@ -24,7 +24,7 @@ PY_ROOTS = ["predictor.py", "demo.py", "demo_utils.py", "utils.py", "visualize.p
             "inference", "dad_3dheads_benchmark"]
 # data the compiled code opens relative to __file__ / cwd
 DATA = ["dad_3dnet.yaml", "model_training/model/backbone.yaml", "model_training/model/static", "model_training/config",
-        "images/demo_heads/1.jpeg", "dad_3dheads_benchmark/data"]
+        "images/demo_heads/1.jpeg", "dad_3dheads_benchmark/data/static"]
 SKIP_DATA_SUFFIX = (".py", ".pyc")
 
 

@@ -102,15 +102,55 @@ def trace_checkpoint(state_dict: Dict[str, Any], path: str) -> str:
     return path
 
 
+class cpu_only:
+    """Context manager: the reference sees a CPU-only host (``torch.cuda.is_available() -> False``), so its own ``to_device``
+    (model/utils.py:31-34) keeps model and tensors on the CPU.  On a GPU box the reference would otherwise run its TorchScript
+    module through cuDNN with TF32 convolutions -- a different arithmetic (~1e-3 off its own fp32 CPU path) and not the
+    CPU baseline this tier compares against.  The reference code itself stays unmodified."""
+
+    def __enter__(self):
+        import torch
+        self._orig = torch.cuda.is_available
+        torch.cuda.is_available = lambda: False
+        return self
+
+    def __exit__(self, *exc):
+        import torch
+        torch.cuda.is_available = self._orig
+        return False
+
+
+class _CpuPredictor:
+    """The reference predictor with every call made under :class:`cpu_only` (attribute access is forwarded)."""
+
+    def __init__(self, inner):
+        object.__setattr__(self, "_inner", inner)
+
+    def __call__(self, *a, **k):
+        with cpu_only():
+            return self._inner(*a, **k)
+
+    def __getattr__(self, name):
+        attr = getattr(self._inner, name)
+        if callable(attr) and name in ("preprocess", "process", "postprocess"):
+            def wrapped(*a, **k):
+                with cpu_only():
+                    return attr(*a, **k)
+            return wrapped
+        return attr
+
+
 def predictor(state_dict: Dict[str, Any], workdir: Optional[str] = None):
-    """The reference's ``FaceMeshPredictor`` (predictor.py:68-211) over a checkpoint traced from ``state_dict``; CPU."""
+    """The reference's ``FaceMeshPredictor`` (predictor.py:68-211) over a checkpoint traced from ``state_dict``, pinned to
+    the CPU (see :class:`cpu_only`)."""
     activate()
     import predictor as ref_predictor
     from utils import load_yaml
     config = load_yaml(os.path.join(_active_root, "dad_3dnet.yaml"))
     workdir = workdir or tempfile.mkdtemp(prefix="dad3d_ref_")
     config["model_path"] = trace_checkpoint(state_dict, os.path.join(workdir, "dad_3dheads.trcd"))   # absolute: join keeps it
-    return ref_predictor.FaceMeshPredictor(config)
+    with cpu_only():
+        return _CpuPredictor(ref_predictor.FaceMeshPredictor(config))
 
 
 # ---------------------------------------------------------------------------------------------------------- decoder
