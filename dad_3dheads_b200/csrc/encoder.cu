@@ -89,6 +89,8 @@ struct Step {
   int up2 = 0;                  // output stored 2x nearest-up-sampled ([N, 2Ho, 2Wo, C])
   int parity = 0;               // 1 + 2a + b: 1x1 conv over the input pixels (2i + a, 2j + b) only, output stored to the same
                                 // pixels of the full-resolution tensor; the residual (res) lives on the half-resolution grid
+  int variant = 0;              // 0: always run; 1: only when the heat-map is requested; 2: only when it is not
+  int sparse_rows = 0;          // heat-map head restricted to the output rows the FusionLayer's bilinear resampling reads
   int stem = 0;                 // the stem as a GEMM: input = space-to-depth image, A map = overlapping 4-pixel windows
   GemmMaps maps;
   GemmGeom geom;
@@ -104,7 +106,7 @@ struct Plan {
   size_t ws_bytes = 0;
   std::vector<TensorInfo> tensors;
   std::vector<Step> steps;
-  int t_mlp_out = -1, t_heat = -1;
+  int t_mlp_out = -1, t_heat = -1, t_c4 = -1;
 };
 
 }  // namespace
@@ -128,6 +130,7 @@ struct dad3d_encoder {
   int halo_cluster = 1;            // env DAD3D_HALO_CLUSTER=2: halo layers run as clusters of 2 row tiles that multicast the weights
   bool kernels_configured = false, stem_configured = false;   // cudaFuncSetAttribute done on this handle's device
   bool td_parity = false;          // env DAD3D_TD_PARITY=1: large top-down nodes as four parity launches
+  bool heat_sparse = true;         // env DAD3D_HEAT_SPARSE=0: always compute the full heat-map
   bool use_pair = false;           // env DAD3D_PAIR=1: cta_group::2 CTA pairs for the large 128-wide layers
   bool use_pdl = false;            // programmatic dependent launch for the tile-engine kernels (env DAD3D_PDL=1 enables;
                                    // measured neutral on B200 at batch 64: 6689 vs 6764 heads/s, so off by default)
@@ -177,7 +180,8 @@ struct Builder {
   // res_mode: 0 none, 1 residual add, 2 gate multiply, 4 second 1x1 source (stride res_stride) whose weights are
   // K-concatenated behind the layer's own; up2: the output is written nearest-up-sampled by 2
   int conv(const std::string& name, int in, int stride, int pad, bool relu, int res = -1, int res_mode = 0,
-           bool f32_out = false, bool pieces_out = true, int* f32_id = nullptr, int res_stride = 1, bool up2 = false) {
+           bool f32_out = false, bool pieces_out = true, int* f32_id = nullptr, int res_stride = 1, bool up2 = false,
+           int variant = 0, int reuse_f32 = -1, bool sparse_rows = false) {
     const ConvW* w = W(name);
     const TensorInfo ti = plan->tensors[in];
     const int Ho = (ti.H + 2 * pad - w->R) / stride + 1;
@@ -195,7 +199,9 @@ struct Builder {
     s.res_stride = res_stride;
     s.up2 = up2 ? 1 : 0;
     s.out = pieces_out ? tensor(ti.N, up2 ? 2 * Ho : Ho, up2 ? 2 * Wo : Wo, w->cout_pad) : -1;
-    s.out_f32 = f32_out ? tensor(ti.N, Ho, Wo, w->cout_pad, true) : -1;
+    s.out_f32 = f32_out ? (reuse_f32 >= 0 ? reuse_f32 : tensor(ti.N, Ho, Wo, w->cout_pad, true)) : -1;
+    s.variant = variant;
+    s.sparse_rows = sparse_rows ? 1 : 0;
     if (s.out >= 0) plan->tensors[s.out].name = name;
     if (s.out_f32 >= 0) plan->tensors[s.out_f32].name = name + (pieces_out ? ".f32" : "");
     if (f32_id) *f32_id = s.out_f32;
@@ -341,9 +347,16 @@ int build_graph(Builder& b) {
   }
   // ---- heat-map head (flame_regression.py:22-25): 3x3 conv 256 -> 68 (+bias), kept in fp32
   int t_heat = -1;
-  b.conv("heat", feat[0], 1, 1, false, -1, 0, /*f32_out=*/true, /*pieces_out=*/false, &t_heat);
+  // Two variants of the same layer: the full 64 x 64 map when the caller asks for the heat-map, otherwise only the output
+  // rows that FusionLayer's align_corners bilinear 64 -> 16 resampling reads (31 of 64: the rows floor(i * 63 / 15) and the
+  // next one) -- env DAD3D_HEAT_SPARSE=0 keeps the full map always.
+  const bool heat_sparse = b.enc->heat_sparse;
+  b.conv("heat", feat[0], 1, 1, false, -1, 0, /*f32_out=*/true, /*pieces_out=*/false, &t_heat, 1, false, heat_sparse ? 1 : 0);
+  if (heat_sparse)
+    b.conv("heat", feat[0], 1, 1, false, -1, 0, /*f32_out=*/true, /*pieces_out=*/false, nullptr, 1, false, 2, t_heat, true);
   plan->t_heat = t_heat;
   // ---- FusionLayer (flame_regression.py:33-42)
+  plan->t_c4 = c4;
   const TensorInfo tc4 = plan->tensors[c4];
   const int t_cat = b.tensor(B, tc4.H, tc4.W, 1024 + kHeatCat + kNumFilters);
   plan->tensors[t_cat].name = "cat";
@@ -469,9 +482,25 @@ int make_plan(dad3d_encoder* enc, int B, void* ws, size_t ws_bytes, bool layout_
       probe.nA = enc->P; probe.nB = enc->P; probe.block_n = w->block_n;
       halo = gemm_halo_b_stages(probe) >= 2;
     }
+    if (s.sparse_rows) halo = false;                  // row-pair tiles (2 rows x 64 columns) through the per-tap path
     if (halo) { g.tw = kHaloTW; g.th = kHaloTH; g.tn = 1; }
     g.tiles_w = ceil_div(Wo, g.tw);
     g.tiles_h = ceil_div(Ho, g.th);
+    if (s.sparse_rows) {
+      // FusionLayer: F.interpolate(heatmap, size=(16, 16), mode="bilinear", align_corners=True) reads source rows
+      // y0 = floor(i * (Ho - 1) / 15) and min(y0 + 1, Ho - 1), i = 0..15 (flame_regression.py:33-41)
+      g.tw = Wo; g.th = 2; g.tn = 1;
+      if (g.tw * g.th != kBlockM) { set_error("sparse heat rows need a 64-pixel-wide map"); return DAD3D_ERR_INVALID; }
+      g.tiles_w = 1;
+      const int Hd = plan->tensors[plan->t_c4].H;      // the FusionLayer's target height (16)
+      g.rowmap_n = 0;
+      for (int i = 0; i < Hd && g.rowmap_n < 32; ++i) {
+        const float fy = (Hd > 1) ? i * (static_cast<float>(Ho - 1) / static_cast<float>(Hd - 1)) : 0.f;   // as fusion_concat_kernel
+        const int y0 = static_cast<int>(fy);
+        if (g.rowmap_n == 0 || g.rowmap[g.rowmap_n - 1] != y0) g.rowmap[g.rowmap_n++] = static_cast<unsigned char>(y0);
+      }
+      g.tiles_h = g.rowmap_n;
+    }
     g.tiles_n = ceil_div(ti.N, g.tn);
     g.Wo = Wo; g.Ho = Ho; g.Nimg = ti.N;
     g.stride = s.stride;
@@ -617,7 +646,13 @@ double conv_useful_flops(const Step& s) {
   if (w->name == "fusion") cin -= 60;                       // zero columns that pad the heat-map slot
   if (w->name == "mlp2") cin /= 3.0;                        // block-diagonal: each output sees one 512-wide block
   if (w->name == "stem") return 2.0 * g.Nimg * g.Ho * g.Wo * cout * 147.0;   // the 7x7x3 taps (the rest of K = 256 is zero)
-  return 2.0 * g.Nimg * g.Ho * g.Wo * cout * cin * w->R * w->S;
+  double rows = g.Ho;
+  if (g.rowmap_n > 0) {                                     // only the rows actually computed count as work done
+    rows = 0;
+    for (int i = 0; i < g.rowmap_n; ++i)
+      for (int r = 0; r < g.th; ++r) rows += (g.rowmap[i] + r < g.Ho) ? 1 : 0;
+  }
+  return 2.0 * g.Nimg * rows * g.Wo * cout * cin * w->R * w->S;
 }
 
 int launch_conv(dad3d_encoder* enc, const Step& s, cudaStream_t stream) {
@@ -729,6 +764,8 @@ int dad3d_encoder_create(dad3d_encoder** out, const dad3d_conv_weights* layers, 
     enc->halo_cluster = (e5 && e5[0] == '2') ? 2 : 1;
     const char* e6 = std::getenv("DAD3D_TD_PARITY");
     enc->td_parity = (e6 && e6[0] == '1');
+    const char* e9 = std::getenv("DAD3D_HEAT_SPARSE");
+    enc->heat_sparse = !(e9 && std::atoi(e9) == 0);
     const char* e3 = std::getenv("DAD3D_PAIR");
     enc->use_pair = (e3 && e3[0] == '1');
     const char* e2 = std::getenv("DAD3D_STEM_SIMT");
@@ -949,6 +986,7 @@ int dad3d_encoder_forward(dad3d_encoder* enc, const float* images_d, int32_t B, 
         break;
       }
       case kConv: {
+        if ((s.variant == 1 && !heatmap_d) || (s.variant == 2 && heatmap_d)) break;     // heat-map head: full map / support rows
         int rc = launch_conv(enc, s, stream);
         if (rc != DAD3D_OK) return rc;
         break;

@@ -486,6 +486,292 @@ __global__ void gather_bary_kernel(const float* __restrict__ src, int B, int nv,
 
 }  // namespace dad3d
 
+
+// =================================================================================================== backward
+// dL/d(params) from dL/d(vertices_3d) and / or dL/d(reprojected vertices): what ``loss.backward()`` needs when the reference's
+// losses call HeadMesh (losses/vertices_3d_loss.py:30-47, losses/reprojection_loss.py:22-46, flame_lightning_model.py:329-351).
+// Forward model (layouts without neck / eyeball pose, the released one):
+//     p_s   = scale * (T + S beta + P phi(jaw))                        blend GEMM (recomputed here into a scratch)
+//     out_v = w_r(v) (A0' p_s + t0) + w_j(v) (A2' p_s + t2) + c        [A'|t], c = F(jaw, rot6, J(beta))  (flame_prep_kernel)
+//     proj  = ((out * sc + (tx, ty, 0)) + 1) * image/2,  sc = max(s + 1, 1e-8)
+// Backward:  g_v = gV + (image/2) sc gP;   dp_s = (w_r A0'^T + w_j A2'^T) g_v;   d coef = Basis_s^T dp_s  -- the dense part,
+// a [heads,15104] x [15104,448] tcgen05 GEMM through the tile engine (fp16 hi/lo operands, 3 products);  the cotangents of
+// (A0', t0, A2', t2, c) are per-head sums over the vertices;  the 24-input function F (Rodrigues, kinematic chain, 6-DoF
+// Gram-Schmidt) is differentiated in forward mode, one input direction per lane, and contracted with those cotangents.
+namespace dad3d {
+
+struct Dual {
+  float v, d;
+};
+__device__ __forceinline__ Dual mk(float v, float d = 0.f) { return Dual{v, d}; }
+__device__ __forceinline__ Dual operator+(Dual a, Dual b) { return {a.v + b.v, a.d + b.d}; }
+__device__ __forceinline__ Dual operator-(Dual a, Dual b) { return {a.v - b.v, a.d - b.d}; }
+__device__ __forceinline__ Dual operator-(Dual a) { return {-a.v, -a.d}; }
+__device__ __forceinline__ Dual operator*(Dual a, Dual b) { return {a.v * b.v, fmaf(a.v, b.d, a.d * b.v)}; }
+__device__ __forceinline__ Dual operator*(float a, Dual b) { return {a * b.v, a * b.d}; }
+__device__ __forceinline__ Dual operator/(Dual a, Dual b) {
+  const float q = a.v / b.v;
+  return {q, (a.d - q * b.d) / b.v};
+}
+__device__ __forceinline__ Dual dsqrt(Dual a) {
+  const float s = sqrtf(a.v);
+  return {s, s > 0.f ? 0.5f * a.d / s : 0.f};
+}
+__device__ __forceinline__ Dual dsin(Dual a) { return {sinf(a.v), cosf(a.v) * a.d}; }
+__device__ __forceinline__ Dual dcos(Dual a) { return {cosf(a.v), -sinf(a.v) * a.d}; }
+__device__ __forceinline__ Dual dmaxc(Dual a, float c) { return a.v >= c ? a : mk(c); }      // fmaxf(x, c)
+
+__device__ __forceinline__ void d_rodrigues(const Dual* r, Dual* R) {      // smplx batch_rodrigues, as rodrigues() above
+  const Dual ax = r[0] + mk(1e-8f), ay = r[1] + mk(1e-8f), az = r[2] + mk(1e-8f);
+  const Dual angle = dsqrt(ax * ax + ay * ay + az * az);
+  const Dual x = r[0] / angle, y = r[1] / angle, z = r[2] / angle;
+  const Dual s = dsin(angle), c1 = mk(1.0f) - dcos(angle);
+  R[0] = mk(1.0f) + c1 * (-(z * z) - y * y);
+  R[1] = s * (-z) + c1 * (x * y);
+  R[2] = s * y + c1 * (x * z);
+  R[3] = s * z + c1 * (x * y);
+  R[4] = mk(1.0f) + c1 * (-(z * z) - x * x);
+  R[5] = s * (-x) + c1 * (y * z);
+  R[6] = s * (-y) + c1 * (x * z);
+  R[7] = s * x + c1 * (y * z);
+  R[8] = mk(1.0f) + c1 * (-(y * y) - x * x);
+}
+__device__ __forceinline__ void d_mat3_mul(const Dual* A, const Dual* B, Dual* C) {
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+}
+__device__ __forceinline__ void d_mat3_vec(const Dual* A, const Dual* v, Dual* o) {
+  for (int i = 0; i < 3; ++i) o[i] = A[3 * i] * v[0] + A[3 * i + 1] * v[1] + A[3 * i + 2] * v[2];
+}
+
+// F: (jaw[3], rot6[6], J[15]) -> out[36] = A0'[9] (row-major, 1/basis_scale folded in), t0[3], A2'[9], t2[3], c[3], phi_jaw[9];
+// the same arithmetic as flame_prep_kernel for layouts whose only posed joint is the jaw (FLAME tree -1,0,1,1,1).
+__device__ void head_transforms_dual(const Dual* jaw, const Dual* rot6, const Dual* J, int flags, float inv_scale, Dual* out) {
+  Dual zero3[3] = {mk(0.f), mk(0.f), mk(0.f)};
+  Dual R0[9], R1[9], R2[9];
+  d_rodrigues(zero3, R0);                 // global rotation is not given to lbs (flame.py:205-208); neck pose is zero here
+  d_rodrigues(zero3, R1);
+  Dual jz[3] = {jaw[0], jaw[1], jaw[2]};
+  if (flags & DAD3D_ZERO_JAW) { jz[0] = jz[1] = jz[2] = mk(0.f); }
+  d_rodrigues(jz, R2);
+  for (int e = 0; e < 9; ++e) out[27 + e] = R2[e] - mk((e == 0 || e == 4 || e == 8) ? 1.0f : 0.0f);
+  // kinematic chain: joint 0, 1 (child of 0), 2 (child of 1)
+  Dual GR1[9], GR2[9], Gt0[3], Gt1[3], Gt2[3], rel[3], tmp[3];
+  for (int k = 0; k < 3; ++k) Gt0[k] = J[k];
+  d_mat3_mul(R0, R1, GR1);
+  for (int k = 0; k < 3; ++k) rel[k] = J[3 + k] - J[k];
+  d_mat3_vec(R0, rel, tmp);
+  for (int k = 0; k < 3; ++k) Gt1[k] = tmp[k] + Gt0[k];
+  d_mat3_mul(GR1, R2, GR2);
+  for (int k = 0; k < 3; ++k) rel[k] = J[6 + k] - J[3 + k];
+  d_mat3_vec(GR1, rel, tmp);
+  for (int k = 0; k < 3; ++k) Gt2[k] = tmp[k] + Gt1[k];
+  // 6-DoF rotation (model/utils.py:92-101)
+  Dual R6[9] = {mk(1.f), mk(0.f), mk(0.f), mk(0.f), mk(1.f), mk(0.f), mk(0.f), mk(0.f), mk(1.f)};
+  if (!(flags & DAD3D_ZERO_ROT)) {
+    const Dual* vx = rot6;
+    const Dual* vy = rot6 + 3;
+    const Dual n1 = dmaxc(dsqrt(vx[0] * vx[0] + vx[1] * vx[1] + vx[2] * vx[2]), 1e-12f);
+    const Dual b1[3] = {vx[0] / n1, vx[1] / n1, vx[2] / n1};
+    const Dual c3[3] = {b1[1] * vy[2] - b1[2] * vy[1], b1[2] * vy[0] - b1[0] * vy[2], b1[0] * vy[1] - b1[1] * vy[0]};
+    const Dual n3 = dmaxc(dsqrt(c3[0] * c3[0] + c3[1] * c3[1] + c3[2] * c3[2]), 1e-12f);
+    const Dual b3[3] = {c3[0] / n3, c3[1] / n3, c3[2] / n3};
+    const Dual b2[3] = {-(b1[1] * b3[2] - b1[2] * b3[1]), -(b1[2] * b3[0] - b1[0] * b3[2]), -(b1[0] * b3[1] - b1[1] * b3[0])};
+    for (int r = 0; r < 3; ++r) {
+      R6[3 * r + 0] = b1[r];
+      R6[3 * r + 1] = b2[r];
+      R6[3 * r + 2] = b3[r];
+    }
+  }
+  const Dual* GRs[2] = {R0, GR2};
+  const Dual* Gts[2] = {Gt0, Gt2};
+  const int jidx[2] = {0, 2};
+  for (int q = 0; q < 2; ++q) {
+    Dual rj[3], t[3], AR[9], At[3];
+    d_mat3_vec(GRs[q], &J[3 * jidx[q]], rj);
+    for (int k = 0; k < 3; ++k) t[k] = Gts[q][k] - rj[k];
+    d_mat3_mul(R6, GRs[q], AR);
+    d_mat3_vec(R6, t, At);
+    for (int e = 0; e < 9; ++e) out[12 * q + e] = inv_scale * AR[e];
+    for (int k = 0; k < 3; ++k) out[12 * q + 9 + k] = At[k];
+  }
+  for (int r = 0; r < 3; ++r) out[24 + r] = kMeshOffsetZ * R6[3 * r + 2];
+}
+
+// per head: max |g_v| over the mesh (g = gV + (image/2) sc gP) -> the power-of-two factor that lifts dp into the fp16 range
+__global__ void __launch_bounds__(256)
+flame_bwd_gmax_kernel(const float* __restrict__ gv, const float* __restrict__ gp, int pc, int nv, const float* __restrict__ xf,
+                      float half_img, float* __restrict__ sigma) {
+  const int h = blockIdx.x;
+  const float sc = xf[static_cast<size_t>(h) * kXfFloats + 63] * half_img;
+  float m = 0.f;
+  for (int v = threadIdx.x; v < nv; v += blockDim.x) {
+    float g[3] = {0.f, 0.f, 0.f};
+    if (gv) for (int c = 0; c < 3; ++c) g[c] = gv[(static_cast<size_t>(h) * nv + v) * 3 + c];
+    if (gp) for (int c = 0; c < pc; ++c) g[c] = fmaf(sc, gp[(static_cast<size_t>(h) * nv + v) * pc + c], g[c]);
+    m = fmaxf(m, fmaxf(fabsf(g[0]), fmaxf(fabsf(g[1]), fabsf(g[2]))));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __shared__ float ws[8];
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, ws[w]);
+    int e = 0;
+    float s = 1.f;
+    if (m > 0.f && isfinite(m)) {
+      frexpf(m, &e);                                   // m = f * 2^e, f in [0.5, 1)
+      s = ldexpf(1.f, 10 - e);                         // sigma * m in [512, 1024)
+    }
+    sigma[h] = s;
+  }
+}
+
+constexpr int kBwdPartial = 32;                        // floats per (head, vertex block) partial record
+// per (head, vertex): dp -> fp16 hi/lo rows of D; per-block partial sums of the transform cotangents
+__global__ void __launch_bounds__(256)
+flame_bwd_vertex_kernel(const float* __restrict__ vposed, int ldv, const float* __restrict__ w2, const float* __restrict__ xf,
+                        const float* __restrict__ gv, const float* __restrict__ gp, int pc, int nv, float half_img,
+                        const float* __restrict__ sigma, float basis_scale, __half* __restrict__ d_hi, __half* __restrict__ d_lo,
+                        float* __restrict__ partial) {
+  __shared__ float s_xf[kXfFloats];
+  __shared__ float s_red[8][kBwdPartial];
+  const int h = blockIdx.y;
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (threadIdx.x < kXfFloats) s_xf[threadIdx.x] = xf[static_cast<size_t>(h) * kXfFloats + threadIdx.x];
+  __syncthreads();
+  float acc[30];
+#pragma unroll
+  for (int i = 0; i < 30; ++i) acc[i] = 0.f;
+  if (v < nv) {
+    const float sc = s_xf[63];
+    float g[3] = {0.f, 0.f, 0.f}, gq[3] = {0.f, 0.f, 0.f};
+    if (gv) for (int c = 0; c < 3; ++c) g[c] = gv[(static_cast<size_t>(h) * nv + v) * 3 + c];
+    if (gp) for (int c = 0; c < pc; ++c) gq[c] = half_img * gp[(static_cast<size_t>(h) * nv + v) * pc + c];
+    const float px = vposed[static_cast<size_t>(h) * ldv + 3 * v], py = vposed[static_cast<size_t>(h) * ldv + 3 * v + 1],
+                pz = vposed[static_cast<size_t>(h) * ldv + 3 * v + 2];
+    const float wr = w2[2 * v], wj = w2[2 * v + 1];
+    const float* A0 = s_xf;            // rows [R | t] of joint 0
+    const float* A2 = s_xf + 24;       // joint 2 (jaw)
+    // forward value of the vertex (needed for d sc)
+    float o[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const float a = fmaf(A0[4 * r], px, fmaf(A0[4 * r + 1], py, fmaf(A0[4 * r + 2], pz, A0[4 * r + 3])));
+      const float b = fmaf(A2[4 * r], px, fmaf(A2[4 * r + 1], py, fmaf(A2[4 * r + 2], pz, A2[4 * r + 3])));
+      o[r] = fmaf(wj, b, fmaf(wr, a, s_xf[60 + r]));
+    }
+    acc[27] = gq[0] * o[0] + gq[1] * o[1] + gq[2] * o[2];          // d sc
+    acc[28] = gq[0];                                               // d tx
+    acc[29] = gq[1];                                               // d ty
+#pragma unroll
+    for (int c = 0; c < 3; ++c) g[c] = fmaf(sc, gq[c], g[c]);      // total cotangent of out_v
+    const float p[3] = {px, py, pz};
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        acc[3 * r + c] = wr * g[r] * p[c];                         // G_A0'
+        acc[12 + 3 * r + c] = wj * g[r] * p[c];                    // G_A2'
+      }
+      acc[9 + r] = wr * g[r];                                      // g_t0
+      acc[21 + r] = wj * g[r];                                     // g_t2
+      acc[24 + r] = g[r];                                          // g_c
+    }
+    // dp_s = (w_r A0'^T + w_j A2'^T) g, lifted by sigma * basis_scale into the fp16 range
+    const float lift = sigma[h] * basis_scale;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float d = wr * (A0[c] * g[0] + A0[4 + c] * g[1] + A0[8 + c] * g[2]) + wj * (A2[c] * g[0] + A2[4 + c] * g[1] + A2[8 + c] * g[2]);
+      split_store(d_hi, d_lo, static_cast<size_t>(h) * ldv + 3 * v + c, d * lift);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 30; ++i) {
+    float x = acc[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5][i] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < 30) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += s_red[w][threadIdx.x];
+    partial[(static_cast<size_t>(h) * gridDim.x + blockIdx.x) * kBwdPartial + threadIdx.x] = s;
+  }
+}
+
+// one warp per head: lanes 0..23 differentiate F along one input each (jaw 0..2, rot6 3..8, J 9..23)
+__global__ void __launch_bounds__(128)
+flame_bwd_finalize_kernel(const float* __restrict__ params, int B, FlameLayoutDev L, const float* __restrict__ jt,
+                          const float* __restrict__ jdirsT, int flags, float inv_scale, const float* __restrict__ dcoef,
+                          const float* __restrict__ partial, int n_blocks, const float* __restrict__ sigma, float basis_scale,
+                          float* __restrict__ gparams) {
+  const int h = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (h >= B) return;
+  const float* p = params + static_cast<size_t>(h) * L.n_params;
+  // joints J = J_T + J_dirs beta (as flame_prep_kernel)
+  float accj[15];
+#pragma unroll
+  for (int j = 0; j < 15; ++j) accj[j] = 0.f;
+  for (int l = lane; l < kBetas; l += 32) {
+    float b = 0.f;
+    if (l < kMaxShape) { if (l < L.n_shape) b = p[L.off_shape + l]; }
+    else if (l - kMaxShape < L.n_expr) b = p[L.off_expr + l - kMaxShape];
+#pragma unroll
+    for (int j = 0; j < 15; ++j) accj[j] = fmaf(b, __ldg(&jdirsT[j * kBetas + l]), accj[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 15; ++j) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) accj[j] += __shfl_xor_sync(0xffffffffu, accj[j], o);
+    accj[j] += __ldg(&jt[j]);
+  }
+  // cotangents: lane i < 30 sums partial[.][i] over the vertex blocks
+  float cot = 0.f;
+  if (lane < 30)
+    for (int b = 0; b < n_blocks; ++b) cot += partial[(static_cast<size_t>(h) * n_blocks + b) * kBwdPartial + lane];
+  const float unlift = 1.0f / (sigma[h] * basis_scale);
+  const float* dc = dcoef + static_cast<size_t>(h) * kKPad;
+  // directional derivative along input `lane`
+  float grad_in = 0.f;
+  {
+    Dual jaw[3], rot6[6], J[15], out[36];
+    for (int k = 0; k < 3; ++k) jaw[k] = mk(L.n_jaw == 3 ? p[L.off_jaw + k] : 0.f, lane == k ? 1.f : 0.f);
+    for (int k = 0; k < 6; ++k) rot6[k] = mk(p[L.off_rot + k], lane == 3 + k ? 1.f : 0.f);
+    for (int k = 0; k < 15; ++k) J[k] = mk(accj[k], lane == 9 + k ? 1.f : 0.f);
+    head_transforms_dual(jaw, rot6, J, flags, inv_scale, out);
+    // out order: A0'[9] t0[3] A2'[9] t2[3] c[3] phi[9]; partial order: G_A0'[9] g_t0[3] G_A2'[9] g_t2[3] g_c[3]
+    for (int i = 0; i < 27; ++i) grad_in = fmaf(__shfl_sync(0xffffffffu, cot, i), out[i].d, grad_in);
+    for (int e = 0; e < 9; ++e) grad_in = fmaf(dc[kBetas + 9 + e] * unlift, out[27 + e].d, grad_in);   // jaw = joint 2: features 9..17
+  }
+  float* gout = gparams + static_cast<size_t>(h) * L.n_params;
+  // betas: dense part + joints part
+  float dJ[15];
+#pragma unroll
+  for (int j = 0; j < 15; ++j) dJ[j] = __shfl_sync(0xffffffffu, grad_in, 9 + j);
+  for (int l = lane; l < kBetas; l += 32) {
+    float gbeta = dc[l] * unlift;
+#pragma unroll
+    for (int j = 0; j < 15; ++j) gbeta = fmaf(dJ[j], __ldg(&jdirsT[j * kBetas + l]), gbeta);
+    if (l < kMaxShape) { if (l < L.n_shape) gout[L.off_shape + l] = gbeta; }
+    else if (l - kMaxShape < L.n_expr) gout[L.off_expr + l - kMaxShape] = gbeta;
+  }
+  if (lane < 3 && L.n_jaw == 3) gout[L.off_jaw + lane] = (flags & DAD3D_ZERO_JAW) ? 0.f : grad_in;
+  if (lane >= 3 && lane < 9) gout[L.off_rot + lane - 3] = (flags & DAD3D_ZERO_ROT) ? 0.f : grad_in;
+  const float dsc = __shfl_sync(0xffffffffu, cot, 27), dtx = __shfl_sync(0xffffffffu, cot, 28), dty = __shfl_sync(0xffffffffu, cot, 29);
+  if (lane == 0) {
+    gout[L.off_scale] = (p[L.off_scale] + 1.0f > 1e-8f) ? dsc : 0.f;      // clamp(s + 1, 1e-8)   head_mesh.py:39
+    gout[L.off_trans + 0] = dtx;
+    gout[L.off_trans + 1] = dty;
+    gout[L.off_trans + 2] = 0.f;                                           // z translation is zeroed in the forward (head_mesh.py:41)
+  }
+}
+
+}  // namespace dad3d
+
 // =================================================================================================== host side
 using namespace dad3d;
 
@@ -507,6 +793,8 @@ struct dad3d_flame {
   CUtensorMap map_b[2];                      // box 64 x 128 (unfused path)
   CUtensorMap map_b96[2];                    // box 64 x 96  (fused path)
   CUtensorMap map_b48[2];                    // box 64 x 48  (fused path, 2x2 clusters: each CTA loads half of a B tile)
+  __half* d_basisT[2] = {nullptr, nullptr};  // [kKPad, npad] hi / lo planes (transposed basis) for the backward GEMM (lazy)
+  CUtensorMap map_bT[2];                     // box 64 x 64 over the transposed planes
   CUtensorMap map_dec[2];                    // hi plane, box 64 x 192 (decode kernel) / 64 x 96 (its CTA-pair variant)
   int fused_chunk = 0;                       // heads per pass of the fused path: 4 row tiles per SM
 };
@@ -852,6 +1140,8 @@ void dad3d_flame_destroy(dad3d_flame* h) {
   cudaFree(h->d_weights);
   cudaFree(h->d_jt);
   cudaFree(h->d_jdirsT);
+  cudaFree(h->d_basisT[0]);
+  cudaFree(h->d_basisT[1]);
   delete h;
 }
 
@@ -980,6 +1270,162 @@ int dad3d_flame_decode(dad3d_flame* h, const float* params_d, int32_t B, int32_t
       count_launch();
       DAD3D_CUDA_OK(cudaGetLastError());
     }
+  }
+  return DAD3D_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ backward host side
+static size_t ws_d_bytes(const dad3d_flame* h, int rows) { return align_up(static_cast<size_t>(rows) * h->npad * sizeof(__half), 1024); }
+static size_t ws_dcoef_bytes(int rows) { return align_up(static_cast<size_t>(rows) * kKPad * sizeof(float), 1024); }
+static size_t ws_partial_bytes(const dad3d_flame* h, int rows) {
+  return align_up(static_cast<size_t>(rows) * ceil_div(h->nv, 256) * kBwdPartial * sizeof(float), 1024);
+}
+
+size_t dad3d_flame_backward_workspace_bytes(const dad3d_flame* h, int32_t B) {
+  if (!h || B <= 0) return 0;
+  const int rows = B < kDecodeChunk ? B : kDecodeChunk;
+  return 2 * ws_coef_bytes(rows) + ws_xf_bytes(rows) + ws_vposed_bytes(h, rows) + 2 * ws_d_bytes(h, rows) + ws_dcoef_bytes(rows) +
+         ws_partial_bytes(h, rows) + align_up(static_cast<size_t>(rows) * sizeof(float), 1024) + 2048;
+}
+
+static int ensure_backward_assets(dad3d_flame* h) {
+  if (h->d_basisT[0]) return DAD3D_OK;
+  const size_t n = static_cast<size_t>(h->npad) * kKPad;
+  std::vector<unsigned short> src(n), dst(n);
+  for (int pl = 0; pl < 2; ++pl) {
+    DAD3D_CUDA_OK(cudaMemcpy(src.data(), h->d_basis[pl], n * 2, cudaMemcpyDeviceToHost));
+    for (int r = 0; r < h->npad; ++r)
+      for (int k = 0; k < kKPad; ++k) dst[static_cast<size_t>(k) * h->npad + r] = src[static_cast<size_t>(r) * kKPad + k];
+    DAD3D_CUDA_OK(cudaMalloc(&h->d_basisT[pl], n * 2));
+    DAD3D_CUDA_OK(cudaMemcpy(h->d_basisT[pl], dst.data(), n * 2, cudaMemcpyHostToDevice));
+    const uint64_t dims[2] = {static_cast<uint64_t>(h->npad), static_cast<uint64_t>(kKPad)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(h->npad) * 2};
+    const uint32_t box[2] = {kBlockK, 64};
+    if (!make_tmap_16bit(&h->map_bT[pl], h->d_basisT[pl], 2, dims, strides, box, nullptr)) return DAD3D_ERR_CUDA;
+  }
+  return DAD3D_OK;
+}
+
+static void hilo_products(GemmGeom& g) {
+  g.nA = 2; g.nB = 2; g.n_mma = 3; g.n_acc = 2;
+  g.mma_a[0] = 1; g.mma_b[0] = 0; g.mma_acc[0] = 1;
+  g.mma_a[1] = 0; g.mma_b[1] = 1; g.mma_acc[1] = 1;
+  g.mma_a[2] = 0; g.mma_b[2] = 0; g.mma_acc[2] = 0;
+}
+
+int dad3d_flame_backward(dad3d_flame* h, const float* params_d, int32_t B, int32_t flags, const float* grad_vertices_d,
+                         const float* grad_projected_d, float image_size, int32_t to_2d, float* grad_params_d,
+                         void* workspace_d, size_t workspace_bytes, dad3d_stream stream_) {
+  DAD3D_REQUIRE(h, "null handle");
+  if (B == 0) return DAD3D_OK;
+  DAD3D_REQUIRE(B > 0 && params_d && grad_params_d, "params / grad_params");
+  DAD3D_REQUIRE(grad_vertices_d || grad_projected_d, "at least one incoming gradient must be given");
+  DAD3D_REQUIRE(h->jaw_only, "backward is implemented for layouts without neck / eyeball pose (the released model)");
+  DAD3D_REQUIRE(workspace_d && workspace_bytes >= dad3d_flame_backward_workspace_bytes(h, B), "workspace too small");
+  int rc = ensure_backward_assets(h);
+  if (rc != DAD3D_OK) return rc;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const int chunk = kDecodeChunk;
+  const int rows_max = B < chunk ? B : chunk;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(workspace_d), 1024));
+  __half* a_hi = reinterpret_cast<__half*>(ws); ws += ws_coef_bytes(rows_max);
+  __half* a_lo = reinterpret_cast<__half*>(ws); ws += ws_coef_bytes(rows_max);
+  float* xf = reinterpret_cast<float*>(ws); ws += ws_xf_bytes(rows_max);
+  float* vposed = reinterpret_cast<float*>(ws); ws += ws_vposed_bytes(h, rows_max);
+  __half* d_hi = reinterpret_cast<__half*>(ws); ws += ws_d_bytes(h, rows_max);
+  __half* d_lo = reinterpret_cast<__half*>(ws); ws += ws_d_bytes(h, rows_max);
+  float* dcoef = reinterpret_cast<float*>(ws); ws += ws_dcoef_bytes(rows_max);
+  float* partial = reinterpret_cast<float*>(ws); ws += ws_partial_bytes(h, rows_max);
+  float* sigma = reinterpret_cast<float*>(ws);
+  const int pc = to_2d ? 2 : 3;
+  const float inv_scale = 1.0f / h->basis_scale;
+  const float half_img = 0.5f * image_size;
+  const int n_blocks = ceil_div(h->nv, 256);
+
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int rows = (B - b0) < chunk ? (B - b0) : chunk;
+    const float* p = params_d + static_cast<size_t>(b0) * h->layout.n_params;
+    const float* gv = grad_vertices_d ? grad_vertices_d + static_cast<size_t>(b0) * h->nv * 3 : nullptr;
+    const float* gp = grad_projected_d ? grad_projected_d + static_cast<size_t>(b0) * h->nv * pc : nullptr;
+    float* gout = grad_params_d + static_cast<size_t>(b0) * h->layout.n_params;
+    flame_prep_kernel<<<ceil_div(rows * 32, 256), 256, 0, stream>>>(p, rows, h->layout, h->d_jt, h->d_jdirsT, flags, inv_scale,
+                                                                     a_hi, a_lo, xf);
+    count_launch();
+    DAD3D_CUDA_OK(cudaGetLastError());
+    {   // forward blend product (recomputed): v_posed * basis_scale -> scratch
+      GemmMaps maps;
+      std::memset(&maps, 0, sizeof(maps));
+      __half* planes[2] = {a_hi, a_lo};
+      for (int pi = 0; pi < 2; ++pi) {
+        const uint64_t dims[4] = {static_cast<uint64_t>(kKPad), static_cast<uint64_t>(rows), 1, 1};
+        const uint64_t strides[3] = {static_cast<uint64_t>(kKPad) * 2, static_cast<uint64_t>(kKPad) * 2 * rows,
+                                     static_cast<uint64_t>(kKPad) * 2 * rows};
+        const uint32_t box[4] = {kBlockK, kBlockM, 1, 1};
+        if (!make_tmap_16bit(&maps.a[pi], planes[pi], 4, dims, strides, box, nullptr)) return DAD3D_ERR_CUDA;
+        maps.b[pi] = h->map_b[pi];
+      }
+      GemmGeom g;
+      std::memset(&g, 0, sizeof(g));
+      g.tw = kBlockM; g.th = 1; g.tn = 1;
+      g.tiles_w = ceil_div(rows, kBlockM); g.tiles_h = 1; g.tiles_n = 1;
+      g.Wo = rows; g.Ho = 1; g.Nimg = 1;
+      g.stride = 1; g.R = 1; g.S = 1;
+      g.cin_blocks = kKPad / kBlockK;
+      g.cl_m = 1; g.cl_n = 1;
+      g.block_n = kBlendBlockN;
+      g.n_tiles = ceil_div(h->n3, kBlendBlockN);
+      hilo_products(g);
+      g.sched = 0;
+      g.stages = gemm_max_stages(g);
+      EpiBlend::Params ep{vposed, h->npad};
+      rc = launch_tile_gemm<EpiBlend>(maps, g, ep, h->num_sms, stream, &h->smem_configured[1], &h->max_clusters[0]);
+      if (rc != DAD3D_OK) return rc;
+    }
+    flame_bwd_gmax_kernel<<<rows, 256, 0, stream>>>(gv, gp, pc, h->nv, xf, half_img, sigma);
+    count_launch();
+    DAD3D_CUDA_OK(cudaGetLastError());
+    DAD3D_CUDA_OK(cudaMemsetAsync(d_hi, 0, static_cast<size_t>(rows) * h->npad * sizeof(__half), stream));
+    DAD3D_CUDA_OK(cudaMemsetAsync(d_lo, 0, static_cast<size_t>(rows) * h->npad * sizeof(__half), stream));
+    {
+      dim3 grid(n_blocks, rows);
+      flame_bwd_vertex_kernel<<<grid, 256, 0, stream>>>(vposed, h->npad, h->d_w2, xf, gv, gp, pc, h->nv, half_img, sigma,
+                                                        h->basis_scale, d_hi, d_lo, partial);
+      count_launch();
+      DAD3D_CUDA_OK(cudaGetLastError());
+    }
+    {   // the dense part: d coef [rows, 448] = D [rows, 15104] x Basis_s [15104, 448]   (tcgen05, fp16 hi/lo, 3 products)
+      GemmMaps maps;
+      std::memset(&maps, 0, sizeof(maps));
+      __half* planes[2] = {d_hi, d_lo};
+      for (int pi = 0; pi < 2; ++pi) {
+        const uint64_t dims[4] = {static_cast<uint64_t>(h->npad), static_cast<uint64_t>(rows), 1, 1};
+        const uint64_t strides[3] = {static_cast<uint64_t>(h->npad) * 2, static_cast<uint64_t>(h->npad) * 2 * rows,
+                                     static_cast<uint64_t>(h->npad) * 2 * rows};
+        const uint32_t box[4] = {kBlockK, kBlockM, 1, 1};
+        if (!make_tmap_16bit(&maps.a[pi], planes[pi], 4, dims, strides, box, nullptr)) return DAD3D_ERR_CUDA;
+        maps.b[pi] = h->map_bT[pi];
+      }
+      GemmGeom g;
+      std::memset(&g, 0, sizeof(g));
+      g.tw = kBlockM; g.th = 1; g.tn = 1;
+      g.tiles_w = ceil_div(rows, kBlockM); g.tiles_h = 1; g.tiles_n = 1;
+      g.Wo = rows; g.Ho = 1; g.Nimg = 1;
+      g.stride = 1; g.R = 1; g.S = 1;
+      g.cin_blocks = h->npad / kBlockK;
+      g.cl_m = 1; g.cl_n = 1;
+      g.block_n = 64;
+      g.n_tiles = kKPad / 64;
+      hilo_products(g);
+      g.sched = 0;
+      g.stages = gemm_max_stages(g);
+      EpiBlend::Params ep{dcoef, kKPad};
+      rc = launch_tile_gemm<EpiBlend>(maps, g, ep, h->num_sms, stream, &h->smem_configured[1], &h->max_clusters[0]);
+      if (rc != DAD3D_OK) return rc;
+    }
+    flame_bwd_finalize_kernel<<<ceil_div(rows * 32, 128), 128, 0, stream>>>(p, rows, h->layout, h->d_jt, h->d_jdirsT, flags, inv_scale,
+                                                                           dcoef, partial, n_blocks, sigma, h->basis_scale, gout);
+    count_launch();
+    DAD3D_CUDA_OK(cudaGetLastError());
   }
   return DAD3D_OK;
 }

@@ -97,6 +97,9 @@ struct GemmGeom {
                                    // [r*block_n/2, (r+1)*block_n/2) of the B tile only; the leader (rank 0) issues every
                                    // MMA (M = 256) and owns the full / tmem-empty barriers.  Operand bytes per CTA:
                                    // A + B/2.  Requires cl_m == cl_n == 1, block_n == 128, sched 0.
+  int rowmap_n;                    // > 0: only `rowmap_n` groups of th output rows are computed; tile row index ih maps to
+  unsigned char rowmap[32];        // first output row rowmap[ih] (tiles_h == rowmap_n).  Used for the heat-map head when only the
+                                   // bilinear support of the FusionLayer's 64 -> 16 resampling is needed (flame_regression.py:33-41)
   int sched;                       // 0: tiles round-robin over CTAs with the column tile fastest (default);
                                    // 1: row-tile persistent -- CTA b owns row tiles b, b+grid, ... and walks ALL column
                                    //    tiles of each (per-row-tile epilogue state is loaded once; all CTAs sweep the
@@ -145,7 +148,7 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmGeom& g, int m_tile, 
   int ih = (c.m_tile / g.tiles_w) % g.tiles_h;
   int in = c.m_tile / (g.tiles_w * g.tiles_h);
   c.n0 = in * g.tn;
-  c.h0 = ih * g.th;
+  c.h0 = g.rowmap_n > 0 ? static_cast<int>(g.rowmap[ih]) : ih * g.th;
   c.w0 = iw * g.tw;
   return c;
 }

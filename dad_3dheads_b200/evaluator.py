@@ -47,6 +47,7 @@ class DADEvaluatorGPU:
 
     # ------------------------------------------------------------------ thin wrappers over the C ABI
     def _gather(self, src: Tensor, idx: Tensor) -> Tensor:
+        src = src.contiguous()
         B, V, nc = src.shape
         out = torch.empty(B, idx.numel(), nc, dtype=torch.float32, device=self.device)
         _lib.check(self.lib.dad3d_gather_landmarks(src.data_ptr(), B, V, nc, idx.data_ptr(), idx.numel(), out.data_ptr(),
@@ -54,6 +55,7 @@ class DADEvaluatorGPU:
         return out
 
     def _lm68(self, verts: Tensor) -> Tensor:
+        verts = verts.contiguous()
         B, V, nc = verts.shape
         out = torch.empty(B, 68, nc, dtype=torch.float32, device=self.device)
         _lib.check(self.lib.dad3d_gather_landmarks_bary(verts.data_ptr(), B, V, nc, self.tri.data_ptr(), self.bary.data_ptr(),
@@ -62,25 +64,29 @@ class DADEvaluatorGPU:
 
     def _align(self, verts: Tensor, scale: Tensor, rot: Tensor, trans: Tensor) -> Tensor:
         B, V, _ = verts.shape
+        # keep every contiguous copy alive until the launch has been enqueued: a temporary released between two
+        # ``.contiguous()`` calls hands its block straight to the next one (same stream), which would overwrite it
+        verts, scale, rot, trans = verts.contiguous(), scale.contiguous(), rot.contiguous(), trans.contiguous()
         out = torch.empty_like(verts)
-        _lib.check(self.lib.dad3d_eval_align(verts.data_ptr(), V, B, scale.contiguous().data_ptr(), rot.contiguous().data_ptr(),
-                                             trans.contiguous().data_ptr(), out.data_ptr(), _stream(self.device)),
-                   "dad3d_eval_align")
+        _lib.check(self.lib.dad3d_eval_align(verts.data_ptr(), V, B, scale.data_ptr(), rot.data_ptr(), trans.data_ptr(),
+                                             out.data_ptr(), _stream(self.device)), "dad3d_eval_align")
         return out
 
     def chamfer_one_sided(self, a: Tensor, b: Tensor) -> Tensor:
         B = a.shape[0]
+        a, b = a.contiguous(), b.contiguous()
         out = torch.empty(B, dtype=torch.float32, device=self.device)
-        _lib.check(self.lib.dad3d_eval_chamfer(a.contiguous().data_ptr(), a.shape[1], b.contiguous().data_ptr(), b.shape[1], B,
-                                               out.data_ptr(), _stream(self.device)), "dad3d_eval_chamfer")
+        _lib.check(self.lib.dad3d_eval_chamfer(a.data_ptr(), a.shape[1], b.data_ptr(), b.shape[1], B, out.data_ptr(),
+                                               _stream(self.device)), "dad3d_eval_chamfer")
         return out
 
     def calc_zn(self, pred: Tensor, gt: Tensor, top_k: int = 5) -> Tensor:
         """[B,K,3] x2 -> [B] (benchmark.py:110-138, its index selection included)."""
         B, K, _ = gt.shape
+        pred, gt = pred.contiguous(), gt.contiguous()
         out = torch.empty(B, dtype=torch.float32, device=self.device)
-        _lib.check(self.lib.dad3d_eval_zn(pred.contiguous().data_ptr(), gt.contiguous().data_ptr(), K, B, top_k,
-                                          out.data_ptr(), _stream(self.device)), "dad3d_eval_zn")
+        _lib.check(self.lib.dad3d_eval_zn(pred.data_ptr(), gt.data_ptr(), K, B, top_k, out.data_ptr(), _stream(self.device)),
+                   "dad3d_eval_zn")
         return out
 
     # ------------------------------------------------------------------ the four metrics, batched

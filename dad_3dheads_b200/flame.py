@@ -179,6 +179,35 @@ class FlameDecoder:
                                                    stream), "dad3d_flame_decode")
         return v3, pj
 
+    def backward(self, params: Tensor, grad_vertices: Optional[Tensor], grad_projected: Optional[Tensor], *, to_2d: bool = True,
+                 zero_rot: bool = False, zero_jaw: bool = False, image_size: float = 256.0) -> Tensor:
+        """d L / d params [B, num_params] from d L / d vertices3d [B,V,3] and / or d L / d projected [B,V,2|3] (either may be
+        None): the backward of :meth:`decode` (csrc/flame.cu ``dad3d_flame_backward``; dense part on tcgen05)."""
+        assert params.is_cuda and params.dtype == torch.float32 and params.ndim == 2 and params.shape[1] == self.num_params
+        assert grad_vertices is not None or grad_projected is not None
+        params = params.contiguous()
+        B = params.shape[0]
+        out = torch.zeros(B, self.num_params, dtype=torch.float32, device=params.device)
+        if B == 0:
+            return out
+        gv = grad_vertices.to(torch.float32).contiguous() if grad_vertices is not None else None
+        gp = grad_projected.to(torch.float32).contiguous() if grad_projected is not None else None
+        if gv is not None:
+            assert gv.shape == (B, self.n_vertices, 3)
+        if gp is not None:
+            assert gp.shape == (B, self.n_vertices, 2 if to_2d else 3)
+        flags = (_lib.DAD3D_ZERO_ROT if zero_rot else 0) | (_lib.DAD3D_ZERO_JAW if zero_jaw else 0)
+        nbytes = int(self.lib.dad3d_flame_backward_workspace_bytes(self._h, B))
+        ws = self._ws.get(params.device, nbytes)
+        stream = torch.cuda.current_stream(params.device).cuda_stream
+        with torch.cuda.device(params.device):
+            _lib.check(self.lib.dad3d_flame_backward(self._h, params.data_ptr(), B, flags,
+                                                     gv.data_ptr() if gv is not None else None,
+                                                     gp.data_ptr() if gp is not None else None, float(image_size),
+                                                     1 if to_2d else 0, out.data_ptr(), ws.data_ptr(), ws.numel(), stream),
+                       "dad3d_flame_backward")
+        return out
+
     def gather(self, src: Tensor, idx: Tensor) -> Tensor:
         """out[b,l,:] = src[b, idx[l], :]  (demo_utils.py:37-47 np.take)."""
         assert src.is_cuda and src.ndim == 3 and src.dtype == torch.float32
@@ -212,6 +241,27 @@ class FlameDecoder:
                                                             torch.cuda.current_stream(src.device).cuda_stream),
                        "dad3d_gather_landmarks_bary")
         return out
+
+
+class DecodeFunction(torch.autograd.Function):
+    """``(vertices3d, projected) = decode(params)`` with a hand-written backward: makes the GPU decoder usable under autograd
+    (training-side callers: losses/vertices_3d_loss.py:30-47, losses/reprojection_loss.py:22-46).  The forward uses the strict
+    hi/lo blend; the backward is dad3d_flame_backward."""
+
+    @staticmethod
+    def forward(ctx, params: Tensor, decoder: "FlameDecoder", to_2d: bool, zero_rot: bool, image_size: float):
+        p = params.detach().to(torch.float32).contiguous()
+        v3, pj = decoder.decode(p, want_vertices=True, want_projected=True, to_2d=to_2d, zero_rot=zero_rot,
+                                image_size=image_size, hilo=True)
+        ctx.save_for_backward(p)
+        ctx.decoder, ctx.to_2d, ctx.zero_rot, ctx.image_size = decoder, to_2d, zero_rot, image_size
+        return v3, pj
+
+    @staticmethod
+    def backward(ctx, grad_v, grad_p):
+        (p,) = ctx.saved_tensors
+        g = ctx.decoder.backward(p, grad_v, grad_p, to_2d=ctx.to_2d, zero_rot=ctx.zero_rot, image_size=ctx.image_size)
+        return g, None, None, None, None
 
 
 class FLAMELayer(nn.Module):

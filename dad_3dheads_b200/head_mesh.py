@@ -54,6 +54,16 @@ class HeadMesh(nn.Module):
             v3, proj = v3.to(src_device), proj.to(src_device)
         return v3, proj
 
+    def decode_with_grad(self, params_3dmm: Tensor, to_2d: bool = True, zero_rotation: bool = False) -> Tuple[Tensor, Tensor]:
+        """(vertices_3d, reprojected_vertices) as differentiable functions of ``params_3dmm`` [B,413] (a CUDA tensor that
+        requires grad): what the reference's losses obtain from ``HeadMesh.vertices_3d`` / ``reprojected_vertices`` under
+        autograd (losses/vertices_3d_loss.py:30-47, losses/reprojection_loss.py:22-46).  Unlike ``reprojected_vertices`` it does
+        not zero translation z in the caller's tensor (its gradient is zero either way)."""
+        from .flame import DecodeFunction
+        packed = self.flame_params(params_3dmm).packed()
+        dec = self.flame.decoder(packed.device)
+        return DecodeFunction.apply(packed, dec, to_2d, zero_rotation, float(self._image_size))
+
     def adjust_3dmm_to_paddings(self, params_3dmm: Tensor, paddings: List[int]) -> Tensor:
         """head_mesh.py:48-60.  paddings = [pad_top, pad_bottom, pad_left, pad_right] (positive when enlarging)."""
         flame_params = self.flame_params(params_3dmm=params_3dmm)

@@ -90,6 +90,16 @@ DAD3D_API int dad3d_flame_decode(dad3d_flame* h, const float* params_d, int32_t 
 
 /* dad3d_gather_landmarks  replaces np.take(projected_vertices, indices, axis=0) (demo_utils.py:37-47) and
  *   FLAMELayer.indices_2d style subset selection: out[b,l,:] = src[b, idx[l], :].  ncomp = 2 or 3. */
+/* Backward of dad3d_flame_decode: grad_params_d [B, num_params] = d L / d params given
+ * grad_vertices_d [B,V,3] = dL/d(vertices3d) and / or grad_projected_d [B,V,2|3] = dL/d(projected) (either may be NULL).
+ * What autograd gives the reference when its losses call HeadMesh.vertices_3d / reprojected_vertices
+ * (losses/vertices_3d_loss.py:30-47, losses/reprojection_loss.py:22-46, train/flame_lightning_model.py:329-351).  The dense
+ * part (d beta, d pose features) is a tcgen05 GEMM over the transposed basis; layouts without neck / eyeball pose only. */
+DAD3D_API size_t dad3d_flame_backward_workspace_bytes(const dad3d_flame* h, int32_t B);
+DAD3D_API int dad3d_flame_backward(dad3d_flame* h, const float* params_d, int32_t B, int32_t flags, const float* grad_vertices_d,
+                                   const float* grad_projected_d, float image_size, int32_t to_2d, float* grad_params_d,
+                                   void* workspace_d, size_t workspace_bytes, dad3d_stream stream);
+
 DAD3D_API int dad3d_gather_landmarks(const float* src_d, int32_t B, int32_t n_vertices, int32_t ncomp, const int32_t* idx_d,
                            int32_t L, float* out_d, dad3d_stream stream);
 /* barycentric variant (model_training/data/utils.py:120-206 get_68_landmarks): out[b,l,:] = sum_k bary[l,k]*src[b,tri[l,k],:] */
