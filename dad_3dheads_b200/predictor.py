@@ -335,7 +335,7 @@ class BatchStream:
     def __init__(self, predictor: FaceMeshPredictor, shape, dtype=torch.uint8, landmark_subset: Optional[str] = "445",
                  to_2d: bool = True, fast_decode: bool = True, depth: int = 2,
                  keys=("3dmm_params", "points", "3d_vertices", "landmarks_445"), host_results: bool = True,
-                 group=None, gather_keys=("3dmm_params", "3d_vertices", "landmarks_445")):
+                 group=None, gather_keys=("3dmm_params", "3d_vertices", "landmarks_445"), comm=None):
         self.pred = predictor
         dev = predictor.device
         self.device = dev
@@ -343,6 +343,7 @@ class BatchStream:
         self.keys = tuple(keys)
         self.host_results = host_results
         self.group = group
+        self.comm = comm                     # optional distributed.Dad3dComm: the gathers then run through the C ABI's NCCL calls
         self.gather_keys = tuple(gather_keys) if group is not None else ()
         self.compute = torch.cuda.Stream(dev)
         self.copy_in = torch.cuda.Stream(dev)
@@ -397,7 +398,10 @@ class BatchStream:
             with torch.cuda.stream(self.comm):
                 self.comm.wait_event(s["done"])
                 for k in self.gather_keys:
-                    dist.all_gather_into_tensor(s["gathered"][k], s["out"][k], group=self.group)
+                    if self.comm is not None:
+                        self.comm.all_gather(s["out"][k], s["gathered"][k])
+                    else:
+                        dist.all_gather_into_tensor(s["gathered"][k], s["out"][k], group=self.group)
                 s["comm_done"].record(self.comm)
             last = s["comm_done"]
         with torch.cuda.stream(self.copy_out):

@@ -207,6 +207,23 @@ DAD3D_API int dad3d_eval_zn(const float* pred_d, const float* gt_d, int32_t K, i
 DAD3D_API int dad3d_eval_align(const float* verts_d, int32_t nv, int32_t B, const float* scale_d, const float* rot_d,
                                const float* trans_d, float* out_d, dad3d_stream stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Multi-GPU helpers: one process per GPU; images are independent, so the only exchanges are the start-up
+ * broadcast of the constants and the per-batch all-gather of the outputs, both over NCCL (NVLink 5 / NVSwitch).  libnccl is
+ * bound at run time (dlopen: the copy already loaded in the process, e.g. PyTorch's, else the system's).
+ *   dad3d_comm_unique_id : rank 0 creates the 128-byte NCCL id; the host distributes it (any side channel, e.g. a
+ *                          torch.distributed / MPI broadcast of 128 bytes)
+ *   dad3d_comm_init      : every rank joins (collective)
+ *   dad3d_bcast_constants: in-place broadcast of `bytes` bytes of device memory from `root` (FLAME bases, packed weights)
+ *   dad3d_allgather_outputs: recv_d [world * bytes_per_rank] <- every rank's send_d [bytes_per_rank], rank-major
+ *                          (params [B,413], vertices [B,5023,3], landmarks ...) */
+typedef struct dad3d_comm dad3d_comm;
+DAD3D_API int dad3d_comm_unique_id(uint8_t* id128_h);
+DAD3D_API int dad3d_comm_init(dad3d_comm** out, const uint8_t* id128_h, int32_t rank, int32_t world, int32_t device);
+DAD3D_API void dad3d_comm_destroy(dad3d_comm* c);
+DAD3D_API int dad3d_bcast_constants(dad3d_comm* c, void* buf_d, size_t bytes, int32_t root, dad3d_stream stream);
+DAD3D_API int dad3d_allgather_outputs(dad3d_comm* c, const void* send_d, void* recv_d, size_t bytes_per_rank, dad3d_stream stream);
+
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 DAD3D_API unsigned long long dad3d_launch_count(void);
 

@@ -42,6 +42,9 @@ def _worker(rank, world, port, q):
         l6, h6 = shard_range(6, rank, world)
         got = all_gather_outputs({"x": full6[l6:h6]}, ("x",))["x"]
         ok = ok and torch.equal(got, full6)
+        # uneven shards (7 rows over 2 ranks: 4 + 3): padded for the collective, trimmed afterwards
+        got7 = all_gather_outputs({"x": full[lo:hi], "y": full[lo:hi] * 2}, ("x", "y"))
+        ok = ok and torch.equal(got7["x"], full) and torch.equal(got7["y"], full * 2)
         q.put((rank, ok, (lo, hi), full[lo:hi].shape[0]))
     finally:
         dist.destroy_process_group()
