@@ -343,7 +343,7 @@ class BatchStream:
         self.keys = tuple(keys)
         self.host_results = host_results
         self.group = group
-        self.comm = comm                     # optional distributed.Dad3dComm: the gathers then run through the C ABI's NCCL calls
+        self.c_comm = comm                   # optional distributed.Dad3dComm: the gathers then run through the C ABI's NCCL calls
         self.gather_keys = tuple(gather_keys) if group is not None else ()
         self.compute = torch.cuda.Stream(dev)
         self.copy_in = torch.cuda.Stream(dev)
@@ -398,8 +398,8 @@ class BatchStream:
             with torch.cuda.stream(self.comm):
                 self.comm.wait_event(s["done"])
                 for k in self.gather_keys:
-                    if self.comm is not None:
-                        self.comm.all_gather(s["out"][k], s["gathered"][k])
+                    if self.c_comm is not None:
+                        self.c_comm.all_gather(s["out"][k], s["gathered"][k])
                     else:
                         dist.all_gather_into_tensor(s["gathered"][k], s["out"][k], group=self.group)
                 s["comm_done"].record(self.comm)
