@@ -315,7 +315,7 @@ def run_ours(args):
     ms_total = timed(dev_stream, x_dev, args.steps)          # EXACTLY K steps -> `value`
     # a region of >= 1.5 s of the same steps: settled clocks, enough nvidia-smi samples; reported beside the K-step number
     per_step = ms_total / args.steps
-    n_long = max(args.steps, int(1500.0 / max(per_step, 1e-3)) + 1)
+    n_long = max(args.steps, int(1500.0 / max(per_step, 1e-3)) + 1) if not args.quick else args.steps
     n_long_t = torch.tensor([n_long], device=dev)
     if distributed:
         dist.broadcast(n_long_t, 0)
@@ -611,11 +611,15 @@ def main():
     ap.add_argument("--no-strict", action="store_true", help="skip the strict-operand comparison run")
     ap.add_argument("--no-extras", action="store_true", help="skip the decode_microbench / config3 / config4 sub-objects")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="profiling aid (ncu launch lists): no >= 1.5 s region, no sub-objects, "
+                    "no strict-mode run, no CPU baseline -- only warm-up + the K timed steps of both arms")
     ap.add_argument("--workload", default=None, choices=["pipeline", "decode"], help="legacy alias: decode = --config 5")
     args = ap.parse_args()
     if args.workload == "decode":
         args.config = 5
     args = resolve(args)
+    if args.quick:
+        args.no_extras = args.no_strict = args.no_cpu_baseline = True
     if args.impl == "reference":
         run_reference(args)
     elif args.config == 5:
