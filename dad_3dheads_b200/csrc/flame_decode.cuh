@@ -104,53 +104,59 @@ template <int RUN>
 __device__ __forceinline__ void dec_flush_aligned(float* __restrict__ dst, unsigned pitch, const float* __restrict__ stage, int lane,
                                                   unsigned cb, unsigned rho, bool head, bool tail) {
   const int off_min = head ? 0 : -kDecCarry;          // first pass of a column range: nothing in front of the new floats
+  // c_r = (cb + rho r) mod 8 depends on r mod 8 only (8 rho = 0 mod 8): a lane meets 4 row residues in the first part and 2
+  // in each of the others, so the shifts, shared-memory bases, row pointers and head predicates are set up once per flush
   {
-    const int rl = (lane >> 4) * 4, c0 = lane & 15;
+    const int rl = (lane >> 4) * 4, c0 = lane & 15;    // rows rl + {0..3, 8..11, 16..19, 24..27}, 16 columns per row
+    const float* sp[4];
+    float* gp[4];
+    bool ok[4];
 #pragma unroll
-    for (int g = 0; g < 2; ++g) {
+    for (int k = 0; k < 4; ++k) {
+      const int off = c0 - static_cast<int>((cb + rho * (rl + k)) & 7u);
+      sp[k] = stage + (rl + k) * kDecStagePitch + kDecCarry + off;
+      gp[k] = dst + static_cast<size_t>(rl + k) * pitch + off;
+      ok[k] = off >= off_min;
+    }
+    const size_t step8 = static_cast<size_t>(pitch) * 8;
+#pragma unroll
+    for (int g = 0; g < 4; g += 2) {
       float t[8];
-      int off[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int row = (((8 * g + u) >> 2) * 8 + ((8 * g + u) & 3)) + rl;      // rows rl + {0..3, 8..11, 16..19, 24..27}
-        const int c = static_cast<int>((cb + rho * row) & 7u);
-        off[u] = c0 - c;                                                        // column relative to the pass's first new float
-        t[u] = stage[row * kDecStagePitch + kDecCarry + off[u]];
-      }
+      for (int u = 0; u < 8; ++u) t[u] = sp[u & 3][(g + (u >> 2)) * 8 * kDecStagePitch];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int row = (((8 * g + u) >> 2) * 8 + ((8 * g + u) & 3)) + rl;
-        if (off[u] >= off_min) dst[static_cast<size_t>(row) * pitch + off[u]] = t[u];
-      }
+      for (int u = 0; u < 8; ++u)
+        if (ok[u & 3]) gp[u & 3][(g + (u >> 2)) * step8] = t[u];
     }
   }
-  {
-    constexpr int kW = RUN - 16;                       // 8 columns [16,24) of a 24-float run; a 16-float run has none
-    if (kW > 0) {
-      const int rl = (lane >> 3) * 2, c0 = 16 + (lane & 7);
-      float t[8];
-      int off[8];
+  if (RUN > 16) {
+    const int rl = (lane >> 3) * 2, c0 = 16 + (lane & 7);   // rows rl + {0,1, 8,9, 16,17, 24,25}, columns [16,24)
+    const float* sp[2];
+    float* gp[2];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int row = ((u >> 1) * 8 + (u & 1)) + rl;                          // rows rl + {0,1, 8,9, 16,17, 24,25}
-        const int c = static_cast<int>((cb + rho * row) & 7u);
-        off[u] = c0 - c;
-        t[u] = stage[row * kDecStagePitch + kDecCarry + off[u]];
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int row = ((u >> 1) * 8 + (u & 1)) + rl;
-        dst[static_cast<size_t>(row) * pitch + off[u]] = t[u];
-      }
+    for (int k = 0; k < 2; ++k) {
+      const int off = c0 - static_cast<int>((cb + rho * (rl + k)) & 7u);
+      sp[k] = stage + (rl + k) * kDecStagePitch + kDecCarry + off;
+      gp[k] = dst + static_cast<size_t>(rl + k) * pitch + off;
     }
+    const size_t step8 = static_cast<size_t>(pitch) * 8;
+    float t[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) t[u] = sp[u & 1][(u >> 1) * 8 * kDecStagePitch];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) gp[u & 1][(u >> 1) * step8] = t[u];
   }
   if (tail) {                                          // the last c_r floats of the warp's column range (c_r < 8): 4 rows per store
-    const int rl = lane >> 3, k = lane & 7;
+    const int rl = lane >> 3, k8 = lane & 7;           // rows rl + 4 u: residues rl and rl + 4
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int row = 4 * u + rl;
-      const int c = static_cast<int>((cb + rho * row) & 7u);
-      if (k < c) dst[static_cast<size_t>(row) * pitch + RUN - c + k] = stage[row * kDecStagePitch + kDecCarry + RUN - c + k];
+    for (int k = 0; k < 2; ++k) {
+      const int c = static_cast<int>((cb + rho * (rl + 4 * k)) & 7u);
+      if (k8 < c) {
+        const float* sp = stage + (rl + 4 * k) * kDecStagePitch + kDecCarry + RUN - c + k8;
+        float* gp = dst + static_cast<size_t>(rl + 4 * k) * pitch + RUN - c + k8;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) gp[static_cast<size_t>(u) * 8 * pitch] = sp[u * 8 * kDecStagePitch];
+      }
     }
   }
 }

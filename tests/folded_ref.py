@@ -12,11 +12,23 @@ import torch.nn.functional as F
 STAGE_UNITS = (3, 4, 6, 3)
 
 
-def run_folded(x: torch.Tensor, layers, fusion_w: np.ndarray, dtype=torch.float64) -> Dict[str, torch.Tensor]:
-    """x [B,3,256,256] -> dict layer-name -> NCHW activation (true channel counts), plus 'params', 'landmarks', 'heat'."""
-    L = {n: (torch.from_numpy(w).to(dtype).permute(0, 3, 1, 2).contiguous(), torch.from_numpy(b).to(dtype))
+def bf16_round(t: torch.Tensor) -> torch.Tensor:
+    """Round-to-nearest-even to bf16 and back: what storing an activation / weight as ONE bf16 piece does (encoder mode "bf16")."""
+    return t.to(torch.bfloat16).to(t.dtype)
+
+
+def run_folded(x: torch.Tensor, layers, fusion_w: np.ndarray, dtype=torch.float64, quant=None) -> Dict[str, torch.Tensor]:
+    """x [B,3,256,256] -> dict layer-name -> NCHW activation (true channel counts), plus 'params', 'landmarks', 'heat'.
+
+    ``quant`` (e.g. :func:`bf16_round`) emulates a single-piece operand mode: it is applied to the image, to every folded weight
+    and to every activation the engine stores as 16-bit pieces (conv outputs after bias / residual / gate / ReLU, the fused
+    BiFPN sums, the FusionLayer concat, the pooled features); biases, accumulation and the fp32-kept outputs (heat-map, MLP
+    logits) stay unrounded -- the bf16-emulating oracle of BASELINE configs[2]."""
+    Q = quant if quant is not None else (lambda t: t)
+    L = {n: (Q(torch.from_numpy(w).to(dtype)).permute(0, 3, 1, 2).contiguous(), torch.from_numpy(b).to(dtype))
          for n, w, b in layers}
     acts: Dict[str, torch.Tensor] = {}
+    F32_OUT = ("heat", "mlp2")
 
     def conv(name, t, stride=1, pad=0, relu=False, res=None, mul=None):
         w, b = L[name]
@@ -27,10 +39,12 @@ def run_folded(x: torch.Tensor, layers, fusion_w: np.ndarray, dtype=torch.float6
             y = y * mul
         if relu:
             y = F.relu(y)
+        if name not in F32_OUT:
+            y = Q(y)
         acts[name] = y
         return y
 
-    x = x.to(dtype)
+    x = Q(x.to(dtype))
     y = conv("stem", x, 2, 3, True)
     acts["stem_conv"] = y
     y = F.max_pool2d(y, 3, 2, 1)
@@ -72,19 +86,19 @@ def run_folded(x: torch.Tensor, layers, fusion_w: np.ndarray, dtype=torch.float6
         p5td = conv(p + "p5td", p5x, relu=True, res=up(p + "p5td_u", p6td, p5x))
         p4td = conv(p + "p4td", p4x, relu=True, res=up(p + "p4td_u", p5td, p4x))
         p3td = conv(p + "p3td", p3x, relu=True, res=up(p + "p3td_u", p4td, p3x))
-        p4o = conv(p + "p4out", w2[0, 0] * p4x + w2[1, 0] * p4td + w2[2, 0] * near(p3td, p4x), relu=True)
-        p5o = conv(p + "p5out", w2[0, 1] * p5x + w2[1, 1] * p5td + w2[2, 1] * near(p4o, p5x), relu=True)
-        p6o = conv(p + "p6out", w2[0, 2] * p6x + w2[1, 2] * p6td + w2[2, 2] * near(p5o, p6x), relu=True)
-        p7o = conv(p + "p7out", w2[0, 3] * p7x + w2[1, 3] * p7td + w2[2, 3] * near(p6o, p7x), relu=True)
+        p4o = conv(p + "p4out", Q(w2[0, 0] * p4x + w2[1, 0] * p4td + w2[2, 0] * near(p3td, p4x)), relu=True)
+        p5o = conv(p + "p5out", Q(w2[0, 1] * p5x + w2[1, 1] * p5td + w2[2, 1] * near(p4o, p5x)), relu=True)
+        p6o = conv(p + "p6out", Q(w2[0, 2] * p6x + w2[1, 2] * p6td + w2[2, 2] * near(p5o, p6x)), relu=True)
+        p7o = conv(p + "p7out", Q(w2[0, 3] * p7x + w2[1, 3] * p7td + w2[2, 3] * near(p6o, p7x)), relu=True)
         feat = [p3td, p4o, p5o, p6o, p7o]
     heat = conv("heat", feat[0], 1, 1)
     hm = F.interpolate(heat, size=c4.shape[2:], mode="bilinear", align_corners=True).sigmoid()
     pad = torch.zeros(hm.shape[0], 128 - hm.shape[1], *hm.shape[2:], dtype=dtype)
-    cat = torch.cat([c4, hm, pad, feat[2]], 1)
+    cat = torch.cat([c4, Q(hm), pad, feat[2]], 1)
     acts["cat"] = cat
     f = conv("fusion", cat, mul=c4)
     s4 = stage(3, f)
-    gap = F.adaptive_avg_pool2d(s4, 1)
+    gap = Q(F.adaptive_avg_pool2d(s4, 1))
     acts["gap"] = gap
     h = conv("mlp1", gap, relu=True)
     o = conv("mlp2", h).flatten(1)

@@ -99,3 +99,36 @@ def test_config2_batch_512_bf16_encoder(cuda_device):
     sub = pred.predict_batch(x[300:364], landmark_subset="445")
     for k in out:
         assert torch.equal(out[k][300:364], sub[k]), k
+    # parity at the full size: a bf16-EMULATING oracle (folded CPU executor with every stored operand rounded to bf16 like the
+    # engine's single-piece mode) on a subset of the 512 images; the plain fp32 oracle is ~6e-3 away from this mode, the
+    # emulation must be clearly closer (what remains is accumulation order / rounding-boundary flips)
+    from dad_3dheads_b200.encoder import fold_state_dict
+    from tests.folded_ref import bf16_round, run_folded
+    rows = [0, 137, 300, 511]
+    layers, fw = fold_state_dict(synthetic_state_dict(0))
+    emu = run_folded(x[rows], layers, fw, dtype=torch.float32, quant=bf16_round)
+    ref = run_folded(x[rows], layers, fw, dtype=torch.float32)
+    got = out["3dmm_params"][rows].cpu()
+    e_emu, e_ref = _rel(got, emu["params"]), _rel(got, ref["params"])
+    print(f"bf16 B=512 params: relL2 vs bf16-emulating oracle {e_emu:.2e}, vs fp32 oracle {e_ref:.2e}")
+    assert e_emu < 5e-3 and e_emu < 0.7 * e_ref, (e_emu, e_ref)
+
+
+def test_heatmap_fallback_branch_matches_reference(predictor):
+    """predictor.py:109-113: when the model output has no OUTPUT_2D_LANDMARKS the landmarks come from the heat-map arg-max
+    (``unravel_index`` -- which divides by H for both axes, model/utils.py:38-52) times the stride; same values as the
+    reference's own ``_parse_output`` on the same tensors, and the 3DMM-only branch when neither key is present."""
+    from oracle import ref_harness as R
+    g = torch.Generator().manual_seed(3)
+    hm = torch.randn(1, 68, 64, 64, generator=g)
+    p = torch.randn(1, 413, generator=g)
+    lm, p3 = predictor._parse_output({"OUTPUT_3DMM_PARAMS": p.clone(), "OUTPUT_LANDMARKS_HEATMAP": hm.clone()})
+    flat = torch.sigmoid(hm).view(1, 68, -1).argmax(-1)
+    want = torch.stack((flat % 64, flat // 64), -1)[0].numpy().astype(np.float64) * 4.0        # (x, y) * stride
+    assert np.array_equal(lm, want) and torch.equal(p3, p)
+    only = predictor._parse_output({"OUTPUT_3DMM_PARAMS": p.clone()})
+    assert torch.is_tensor(only) and torch.equal(only, p)
+    if R.available():
+        ref = R.predictor(synthetic_state_dict(0))
+        lm_ref, p_ref = ref._parse_output({"OUTPUT_3DMM_PARAMS": p.clone(), "OUTPUT_LANDMARKS_HEATMAP": hm.clone()})
+        assert np.array_equal(lm, lm_ref) and torch.equal(p3, p_ref)
