@@ -224,6 +224,21 @@ DAD3D_API void dad3d_comm_destroy(dad3d_comm* c);
 DAD3D_API int dad3d_bcast_constants(dad3d_comm* c, void* buf_d, size_t bytes, int32_t root, dad3d_stream stream);
 DAD3D_API int dad3d_allgather_outputs(dad3d_comm* c, const void* send_d, void* recv_d, size_t bytes_per_rank, dad3d_stream stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Rasteriser: the reference's native Sim3DR component (Sim3DR/lib/rasterize_kernel.cpp `_rasterize`
+ * :238-292 and `_get_normal` :158-236; callers Sim3DR/Sim3DR.py:8-29, inference/pncc_estimator.py:16-43), bit-exact.
+ *   dad3d_rasterize: z-buffer rendering of per-vertex colours with alpha = 1 (what Sim3DR.rasterize uses): vertices_d [nv,3]
+ *     (x, y in pixels, z = depth, larger wins), triangles_d [ntri,3], colors_d [nv,c] in [0,1]; image_d [h,w,c] uint8 and
+ *     depth_d [h,w] are read-modify-write exactly like the reference's buffers (depth is usually initialised to -1e8);
+ *     key_ws_d = h*w 64-bit words of scratch; reverse != 0 flips the image rows.
+ *   dad3d_vertex_normals: normalised sum of the incident (un-normalised) face normals per vertex; adj_offsets_d [nv+1] /
+ *     adj_triangles_d = CSR list of each vertex's triangles in ascending order (fixed per topology). */
+DAD3D_API int dad3d_rasterize(const float* vertices_d, const int32_t* triangles_d, const float* colors_d, int32_t ntri,
+                              uint8_t* image_d, float* depth_d, unsigned long long* key_ws_d, int32_t h, int32_t w, int32_t c,
+                              int32_t reverse, dad3d_stream stream);
+DAD3D_API int dad3d_vertex_normals(const float* vertices_d, const int32_t* triangles_d, const int32_t* adj_offsets_d,
+                                   const int32_t* adj_triangles_d, int32_t nver, float* normals_d, dad3d_stream stream);
+
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 DAD3D_API unsigned long long dad3d_launch_count(void);
 

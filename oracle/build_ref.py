@@ -70,6 +70,15 @@ def build(ref: str = REF, out: str = OUT) -> bool:
                 if not (os.path.isfile(dst) and os.path.getsize(dst) == os.path.getsize(full)):
                     shutil.copyfile(full, dst)
                 n_data += 1
+    # the reference's one native component on the path's "next" rows: the Sim3DR z-buffer rasteriser (C++), compiled from the
+    # source file where it lies (same flags as its setup.py: -std=c++11, default -O2, no -march) plus our extern "C" shim
+    import subprocess
+    so = os.path.join(out, "libsim3dr_ref.so")
+    src = os.path.join(ref, "Sim3DR", "lib", "rasterize_kernel.cpp")
+    shim = os.path.join(os.path.dirname(os.path.abspath(__file__)), "sim3dr_ref_shim.cpp")
+    if os.path.isfile(src):
+        subprocess.run(["g++", "-O2", "-std=c++11", "-fPIC", "-shared", "-I", os.path.dirname(src), src, shim, "-o", so],
+                       check=True)
     with open(os.path.join(out, "BUILD_INFO.txt"), "w") as f:
         f.write(f"byte-compiled from {ref} by oracle/build_ref.py with python {sys.version.split()[0]}: "
                 f"{n_py} modules, {n_data} data files\n")

@@ -30,7 +30,7 @@ def test_reference_module_paths_resolve():
 def test_reference_demo_modules_import_over_compat():
     """Every symbol the reference's demo.py / demo_utils.py import (demo.py:1-20, demo_utils.py:1-12) resolves with compat/
     first on sys.path: the reference's own demo_utils.py is imported UNCHANGED (source tree here, bytecode twin on the GPU box);
-    only third-party packages the image lacks (fire, pytorch_toolbelt) come from oracle/ref_shims."""
+    only third-party packages the image lacks (fire, pytorch_toolbelt, psbody) come from oracle/ref_shims."""
     import pytest
     from oracle import ref_harness as R
     if not R.available():
@@ -45,7 +45,9 @@ def test_reference_demo_modules_import_over_compat():
         "from pytorch_toolbelt.utils import read_rgb_image\n"
         "from model_training.utils import load_indices_from_npy, get_list_of_npy_files\n"
         "from model_training.model.utils import get_flame_model, get_flame_indices, normalize_to_cube\n"
-        "import model_training.head_mesh, inference.uv_texture, inference.pncc_estimator\n"
+        "import model_training.head_mesh, inference.uv_texture, inference.pncc_estimator, Sim3DR\n"
+        "assert 'compat' in Sim3DR.__file__ and inference.pncc_estimator.Sim3DR is Sim3DR\n"
+        "assert 'compat' not in inference.pncc_estimator.__file__          # the reference's own estimator, not a stub\n"
         "assert 'dad_3dheads_b200' in sys.modules['predictor'].FaceMeshPredictor.__module__\n"
         "assert get_flame_model().v_template.shape == (5023, 3) and get_flame_indices('indices_2d').shape == (191,)\n"
         "import torch\n"

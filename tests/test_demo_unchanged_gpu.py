@@ -1,7 +1,7 @@
 """-m gpu: the reference's OWN demo.py / demo_utils.py, unmodified, over the B200 path (north_star: "keeping
 predictor.FaceMeshPredictor's API so demo.py ... run unchanged").
 
-``sys.path`` = [compat/ (predictor, model_training, inference, utils -> libdad3d.so), oracle/ref_shims (stand-ins for the
+``sys.path`` = [compat/ (predictor, model_training, utils, Sim3DR -> libdad3d.so), oracle/ref_shims (stand-ins for the
 third-party packages demo.py imports that the image lacks: fire, pytorch_toolbelt), the reference tree (demo.py, demo_utils.py
 and its static index files; /root/reference here, its byte-compiled twin oracle/_ref on the GPU box)].  The checkpoint is a
 synthetic-weight ``dad_3dheads.trcd`` written with torch.jit exactly like the reference's exporter
@@ -71,3 +71,41 @@ def test_demo_flame_params_and_landmark_outputs(demo_home, tmp_path):
         img = cv2.imread(str(tmp_path / f"1_{kind}.png"))
         assert img is not None and img.shape == img0.shape
         assert (img != img0).any()                                        # landmarks were drawn
+
+
+def test_demo_pncc_runs_the_reference_estimator_on_the_gpu_rasteriser(demo_home, tmp_path):
+    """``python demo.py ... pncc``: the reference's own inference/pncc_estimator.py (HeadMesh.reprojected_vertices(to_2d=False)
+    -> Sim3DR.rasterize) over compat/ -- the decode and the rasteriser both run in libdad3d.so.  Expected image: the reference's
+    C++ rasteriser (oracle/_ref/libsim3dr_ref.so) on the vertices of the reference predictor's parameters for the same image;
+    the two parameter sets differ by ~1e-5 relative, so a few silhouette pixels may flip (bit-exactness of the rasteriser on
+    identical input is tests/test_rasterizer_gpu.py)."""
+    import cv2
+    import torch
+    from dad_3dheads_b200.flame import load_flame_static
+    from oracle.flame_oracle import FlameOracle
+    _run_demo(demo_home, tmp_path, "pncc")
+    got = cv2.cvtColor(cv2.imread(str(tmp_path / "1_pncc.png")), cv2.COLOR_BGR2RGB)
+    img0 = cv2.imread(os.path.join(R.root(), "images", "demo_heads", "1.jpeg"))
+    assert got.shape == img0.shape
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "ref_shims"))
+    try:
+        import importlib
+        ref_sim = importlib.import_module("Sim3DR")
+        assert "ref_shims" in ref_sim.__file__
+    finally:
+        sys.path.pop(0)
+        sys.modules.pop("Sim3DR", None)
+    z = np.load(os.path.join(ROOT, "tests", "golden", "reference_predictor.npz"))
+    st = load_flame_static()
+    # predictor.py:136-150 scales the parameters' projection back to the input image: rebuild the same vertices from the params
+    p = torch.from_numpy(z["params_3dmm"]).double().clone()
+    v = FlameOracle(st, image_size=256).reprojected_vertices(p, to_2d=False)[0].numpy().astype(np.float32)
+    v[:, 2] *= -1
+    faces = np.load(os.path.join(R.root(), "model_training", "model", "static", "flame_indices", "faces_wo_ears_remapped.npy"))
+    sub = st["v_template"][np.unique(faces)]
+    lo, hi = sub.min(0, keepdims=True, initial=0), sub.max(0, keepdims=True, initial=0)
+    colors = ((st["v_template"] - lo) / (hi - lo)).astype(np.float32)
+    want = ref_sim.rasterize(v, np.ascontiguousarray(faces), colors, bg=np.zeros_like(got))
+    covered = (want.sum(-1) > 0).mean()
+    assert covered > 0.005
+    assert (got != want).any(-1).mean() < 0.03 * covered, ((got != want).any(-1).mean(), covered)

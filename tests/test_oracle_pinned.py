@@ -208,3 +208,34 @@ def test_runtime_flame_pickle_loader_matches_packed_asset():
     for k in ("v_template", "shapedirs", "posedirs", "J_regressor", "parents", "lbs_weights", "faces", "indices_2d"):
         assert a[k].dtype == b[k].dtype and np.array_equal(a[k], b[k]), k
     assert "keypoints_445" in b            # landmark tables still come from the packed asset
+
+
+@needs_ref
+def test_live_pncc_estimator_over_the_references_cpp_rasteriser():
+    """inference/pncc_estimator.py (unmodified) with Sim3DR = the reference's own rasterize_kernel.cpp (oracle/_ref/
+    libsim3dr_ref.so, bound by oracle/ref_shims/Sim3DR): the restatement used as the expected image of the pncc demo test
+    (oracle decode -> flip z -> NCC colours of v_template -> rasterise) reproduces it byte for byte."""
+    so = os.path.join(os.path.dirname(GOLD), "..", "oracle", "_ref", "libsim3dr_ref.so")
+    if not os.path.isfile(so):
+        pytest.skip("oracle/_ref/libsim3dr_ref.so not built")
+    R.activate()
+    import importlib
+    est = importlib.import_module("inference.pncc_estimator").PNCCEstimator()
+    import Sim3DR
+    assert "ref_shims" in Sim3DR.__file__
+    z = np.load(os.path.join(GOLD, "reference_predictor.npz"))
+    p = torch.from_numpy(z["params_3dmm"]).clone()
+    image = np.full((640, 420, 3), 7, np.uint8)          # synthetic weights: the head lands at x 213-379, y 451-600
+    want = est(image, {"3dmm_params": p.clone()}, with_background=True)
+    st = load_static()
+    v = FlameOracle(st, image_size=256).reprojected_vertices(p.clone().double(), to_2d=False)[0].numpy().astype(np.float32)
+    v[:, 2] *= -1
+    faces = est.faces_wo_back_remapped
+    sub = st["v_template"][np.unique(faces)]
+    lo, hi = sub.min(0, keepdims=True, initial=0), sub.max(0, keepdims=True, initial=0)
+    colors = ((st["v_template"] - lo) / (hi - lo)).astype(np.float32)
+    assert np.abs(colors - est.colors).max() < 1e-6
+    got = Sim3DR.rasterize(v, faces, est.colors.astype(np.float32), bg=image.copy())
+    covered = (want != image).any(-1).mean()
+    assert covered > 0.01
+    assert (got != want).any(-1).mean() < 0.02 * covered                     # fp64-oracle vs fp32-reference vertices: edge pixels only
