@@ -8,6 +8,7 @@
 // model_training/head_mesh.py:33-46.  See DESIGN.md for layouts and rooflines.
 #include <cuda_fp16.h>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -913,6 +914,47 @@ int launch_flame_decode(dad3d_flame* h, const __half* a_hi, int rows, const floa
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.numAttrs = 1;
+  }
+  p.prof = nullptr;
+  if (std::getenv("DAD3D_DECODE_PROFILE")) {
+    // diagnostics: the cycle-accounting instantiation, synchronous, table on stderr (never used by the product path)
+    static bool configured[2] = {false, false};
+    if (!configured[kPair ? 1 : 0]) {
+      DAD3D_CUDA_OK(cudaFuncSetAttribute(flame_decode_kernel<kPair, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecSmemLimit));
+      configured[kPair ? 1 : 0] = true;
+    }
+    const int nblk = static_cast<int>(cfg.gridDim.x);
+    const size_t words = static_cast<size_t>(nblk) * 10 * 8;
+    unsigned* d_prof = nullptr;
+    DAD3D_CUDA_OK(cudaMalloc(&d_prof, words * sizeof(unsigned)));
+    DAD3D_CUDA_OK(cudaMemsetAsync(d_prof, 0, words * sizeof(unsigned), stream));
+    p.prof = d_prof;
+    DAD3D_CUDA_OK(cudaLaunchKernelEx(&cfg, flame_decode_kernel<kPair, true>, map_a, h->map_dec[kPair ? 1 : 0], p));
+    count_launch();
+    DAD3D_CUDA_OK(cudaStreamSynchronize(stream));
+    std::vector<unsigned> hp(words);
+    DAD3D_CUDA_OK(cudaMemcpy(hp.data(), d_prof, words * sizeof(unsigned), cudaMemcpyDeviceToHost));
+    cudaFree(d_prof);
+    double prod[8] = {0}, mma[8] = {0}, epi[8] = {0};
+    int n_mma = 0;
+    for (int b = 0; b < nblk; ++b) {
+      for (int k = 0; k < 8; ++k) prod[k] += hp[(static_cast<size_t>(b) * 10 + 0) * 8 + k];
+      if (hp[(static_cast<size_t>(b) * 10 + 1) * 8 + 7]) {
+        ++n_mma;
+        for (int k = 0; k < 8; ++k) mma[k] += hp[(static_cast<size_t>(b) * 10 + 1) * 8 + k];
+      }
+      for (int w = 2; w < 10; ++w)
+        for (int k = 0; k < 8; ++k) epi[k] += hp[(static_cast<size_t>(b) * 10 + w) * 8 + k] / 8.0;
+    }
+    const double nb = nblk, nm = n_mma > 0 ? n_mma : 1;
+    std::fprintf(stderr,
+                 "[decode profile] rows %d pair %d blocks %d stages %d kbs %d splits %d | cycles per CTA (mean)\n"
+                 "  producer: total %.0f  wait_empty_slot %.0f  wait_tile_release %.0f\n"
+                 "  mma     : total %.0f  tiles %.1f  wait_free_accumulator %.0f  wait_full_slot %.0f  wait_coefficients %.0f\n"
+                 "  epilogue: total %.0f  tiles %.1f  wait_full_accumulator %.0f  tmem_ld %.0f  math %.0f  stage+store %.0f (mean of 8 warps)\n",
+                 rows, kPair ? 1 : 0, nblk, p.stages, p.kbs, p.splits, prod[7] / nb, prod[0] / nb, prod[1] / nb, mma[7] / nm, mma[6] / nm,
+                 mma[0] / nm, mma[1] / nm, mma[2] / nm, epi[7] / nb, epi[6] / nb, epi[0] / nb, epi[1] / nb, epi[2] / nb, epi[3] / nb);
+    return DAD3D_OK;
   }
   DAD3D_CUDA_OK(cudaLaunchKernelEx(&cfg, flame_decode_kernel<kPair>, map_a, h->map_dec[kPair ? 1 : 0], p));
   count_launch();

@@ -60,6 +60,7 @@ struct DecodeParams {
   int pc;
   float image_size;
   int poll;                 // 1: producer / MMA warps poll their barriers with test_wait instead of try_wait (A/B)
+  unsigned* prof;           // kProf instantiation only (DAD3D_DECODE_PROFILE): [block][10 warps][8] cycle counters
   int debug;                // diagnostics only (DAD3D_DECODE_DEBUG): 1 = all global stores go to the first 128 rows (L2-resident
                             // footprint: isolates the SM -> L2 store path from DRAM), 2 = stores predicated off at run time, 3 = the epilogue only
                             // hands the accumulator back (pure main-loop rate)
@@ -175,7 +176,12 @@ __device__ __forceinline__ void dec_wait(uint64_t* bar, uint32_t parity, int pol
   else ptx::mbar_wait(bar, parity);
 }
 
-template <bool kPair>
+// kProf: cycle accounting per warp role (clock() deltas summed over the launch), written to p.prof at the end:
+//   producer  [0] waiting for a free ring slot, [1] waiting for the resident tile to be released, [7] whole role
+//   MMA       [0] waiting for a free accumulator (epilogue back-pressure), [1] waiting for a full ring slot (feed starvation),
+//             [2] waiting for the coefficient tile, [6] tiles, [7] whole role
+//   epilogue  [0] waiting for a full accumulator, [1] TMEM loads, [2] skinning math, [3] staging + stores, [6] tiles, [7] whole role
+template <bool kPair, bool kProf = false>
 __global__ void __launch_bounds__(kDecThreads, 1)
 flame_decode_kernel(const __grid_constant__ CUtensorMap map_a,     // coefficients [rows, 448] fp16, box 64 x 128
                     const __grid_constant__ CUtensorMap map_b,     // basis [npad, 448] fp16, box 64 x (192 | 96)
@@ -236,9 +242,13 @@ flame_decode_kernel(const __grid_constant__ CUtensorMap map_a,     // coefficien
     int stage = 0;
     uint32_t phase = 0, aphase = 0;
     int m, n0, n1;
+    unsigned pc0 = 0, pc1 = 0, pt0 = 0, pstart = 0;
+    if constexpr (kProf) pstart = clock();
     for (int ui = 0; dec_unit_at(p, group, n_groups, ui, &m, &n0, &n1); ++ui) {
       // the resident coefficient tile may be overwritten once every MMA of the previous unit has read it
+      if constexpr (kProf) pt0 = clock();
       dec_wait(aempty_bar, aphase ^ 1u, p.poll);
+      if constexpr (kProf) pc1 += clock() - pt0;
       const int row0 = (kPair ? 2 * m + crank : m) * kDecBlockM;
       if (ptx::elect_one_sync()) {
         for (int kb = 0; kb < kDecKBlocks; ++kb) {
@@ -257,7 +267,9 @@ flame_decode_kernel(const __grid_constant__ CUtensorMap map_a,     // coefficien
       for (int n = n0; n < n1; ++n) {
         for (int kb0 = 0; kb0 < kDecKBlocks; kb0 += p.kbs) {
           const int nk = min(p.kbs, kDecKBlocks - kb0);
+          if constexpr (kProf) pt0 = clock();
           dec_wait(&empty_bar[stage], phase ^ 1u, p.poll);
+          if constexpr (kProf) pc0 += clock() - pt0;
           if (ptx::elect_one_sync()) {
             if constexpr (kPair) {
               const uint32_t lead = ptx::mapa_u32(&full_bar[stage], 0);
@@ -277,6 +289,12 @@ flame_decode_kernel(const __grid_constant__ CUtensorMap map_a,     // coefficien
         }
       }
     }
+    if constexpr (kProf) {
+      if (lane == 0) {
+        unsigned* o = p.prof + (static_cast<size_t>(blockIdx.x) * 10 + 0) * 8;
+        o[0] = pc0; o[1] = pc1; o[7] = clock() - pstart;
+      }
+    }
   } else if (warp == 1) {
     // ===================================================== MMA issuer
     if (!kPair || crank == 0) {
@@ -286,16 +304,23 @@ flame_decode_kernel(const __grid_constant__ CUtensorMap map_a,     // coefficien
       int acc = 0;
       uint32_t acc_phase = 0;
       int m, n0, n1;
+      unsigned mc0 = 0, mc1 = 0, mc2 = 0, mt0 = 0, mtiles = 0, mstart = 0;
+      if constexpr (kProf) mstart = clock();
       for (int ui = 0; dec_unit_at(p, group, n_groups, ui, &m, &n0, &n1); ++ui) {
         for (int n = n0; n < n1; ++n) {
+          if constexpr (kProf) mt0 = clock();
           dec_wait(&tempty_bar[acc], acc_phase ^ 1u, p.poll);
+          if constexpr (kProf) { mc0 += clock() - mt0; ++mtiles; }
           ptx::tc_fence_after();
           const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kDecN);
           for (int kb0 = 0; kb0 < kDecKBlocks; kb0 += p.kbs) {
             const int nk = min(p.kbs, kDecKBlocks - kb0);
+            if constexpr (kProf) mt0 = clock();
             if (n == n0)                                             // first sweep over the freshly loaded coefficient tile
               for (int j = 0; j < nk; ++j) dec_wait(&afull_bar[kb0 + j], aphase, p.poll);
+            if constexpr (kProf) { const unsigned t = clock(); mc2 += t - mt0; mt0 = t; }
             dec_wait(&full_bar[stage], phase, p.poll);
+            if constexpr (kProf) mc1 += clock() - mt0;
             ptx::tc_fence_after();
             const uint32_t sa0 = ptx::smem_u32(smem_a + kb0 * kDecABytes);
             const uint32_t sb0 = ptx::smem_u32(smem_b + stage * kBStage);
@@ -330,6 +355,12 @@ flame_decode_kernel(const __grid_constant__ CUtensorMap map_a,     // coefficien
         }
         aphase ^= 1u;
       }
+      if constexpr (kProf) {
+        if (lane == 0) {
+          unsigned* o = p.prof + (static_cast<size_t>(blockIdx.x) * 10 + 1) * 8;
+          o[0] = mc0; o[1] = mc1; o[2] = mc2; o[6] = mtiles; o[7] = clock() - mstart;
+        }
+      }
     }
   } else {
     // ===================================================== epilogue warps
@@ -351,6 +382,8 @@ flame_decode_kernel(const __grid_constant__ CUtensorMap map_a,     // coefficien
     float vprev[8], qprev[8];                      // this row's last 8 floats of the previous pass (the carry), per output
 #pragma unroll
     for (int j = 0; j < 8; ++j) vprev[j] = qprev[j] = 0.f;
+    unsigned ec0 = 0, ec1 = 0, ec2 = 0, ec3 = 0, et0 = 0, etiles = 0, estart = 0;
+    if constexpr (kProf) estart = clock();
     for (int ui = 0; dec_unit_at(p, group, n_groups, ui, &m, &n0, &n1); ++ui) {
       const int head0 = (kPair ? 2 * m + crank : m) * kDecBlockM + wq * 32;
       {   // per-head transforms -> registers, once per unit (rows past the batch read the last valid record; never stored)
@@ -386,7 +419,9 @@ flame_decode_kernel(const __grid_constant__ CUtensorMap map_a,     // coefficien
         const bool tile_full = rows_left >= 32 && (vb + 32) * 3 <= nv3;
         const unsigned cb_v = v_base ? static_cast<unsigned>((reinterpret_cast<uintptr_t>(v_base + vb * 3) >> 2) & 7u) : 0u;
         const unsigned cb_q = q_base ? static_cast<unsigned>((reinterpret_cast<uintptr_t>(q_base + vb * pc) >> 2) & 7u) : 0u;
+        if constexpr (kProf) et0 = clock();
         ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+        if constexpr (kProf) { ec0 += clock() - et0; ++etiles; }
         ptx::tc_fence_after();
         const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + static_cast<uint32_t>(acc * kDecN + grp * 96);
         if (p.debug == 3) {
@@ -397,9 +432,11 @@ flame_decode_kernel(const __grid_constant__ CUtensorMap map_a,     // coefficien
 #pragma unroll 1
         for (int q = 0; q < 4 && p.debug != 3; ++q) {          // 4 passes of 8 vertices (24 accumulator columns)
           float xa[24];
+          if constexpr (kProf) et0 = clock();
           ptx::tmem_ld_32x32b_x16_f(t_acc + q * 24, xa);
           ptx::tmem_ld_32x32b_x8_f(t_acc + q * 24 + 16, xa + 16);
           ptx::tmem_ld_wait();
+          if constexpr (kProf) { const unsigned t = clock(); ec1 += t - et0; et0 = t; }
           if (q == 3) {                              // the warp's share of the accumulator has been read: hand TMEM back
             ptx::tc_fence_before();
             if constexpr (kPair) ptx::mbar_arrive_cluster(acc ? tempty_cluster1 : tempty_cluster0);
@@ -425,6 +462,14 @@ flame_decode_kernel(const __grid_constant__ CUtensorMap map_a,     // coefficien
           }
           const int vfirst = vb + q * 8;
           const int ncols = min(kDecPassCols, nv3 - vfirst * 3);        // valid floats of this pass's run (<= 0: past the mesh)
+          if constexpr (kProf) {
+            // pin the math in front of the second clock read: the staged values depend on it
+            float sink = 0.f;
+#pragma unroll
+            for (int j = 0; j < 24; ++j) sink += x[j];
+            if (sink == 1.2345e-33f) ec2 += 1u;
+            const unsigned t = clock(); ec2 += t - et0; et0 = t;
+          }
           if (ncols <= 0 || rows_left <= 0 || p.debug == 2) continue;
           if (v_base) {
             // staged row = [8 carry floats of the previous pass | 24 new floats]
@@ -481,10 +526,17 @@ flame_decode_kernel(const __grid_constant__ CUtensorMap map_a,     // coefficien
             }
             __syncwarp();
           }
+          if constexpr (kProf) ec3 += clock() - et0;
         }
         vb += kDecN / 3;
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+    if constexpr (kProf) {
+      if (lane == 0) {
+        unsigned* o = p.prof + (static_cast<size_t>(blockIdx.x) * 10 + warp) * 8;
+        o[0] = ec0; o[1] = ec1; o[2] = ec2; o[3] = ec3; o[6] = etiles; o[7] = clock() - estart;
       }
     }
   }
