@@ -84,12 +84,13 @@ __device__ __forceinline__ void split_store(__half* hi, __half* lo, size_t idx, 
 __global__ void __launch_bounds__(256)
 flame_prep_kernel(const float* __restrict__ params, int B, FlameLayoutDev L, const float* __restrict__ jt,
                   const float* __restrict__ jdirsT, int flags, float inv_scale, __half* __restrict__ a_hi,
-                  __half* __restrict__ a_lo, float* __restrict__ xf) {
+                  __half* __restrict__ a_lo, float* __restrict__ xf, int permute) {
   const int h = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (h >= B) return;
   const float* p = params + static_cast<size_t>(h) * L.n_params;
-  const size_t arow = static_cast<size_t>(h) * kKPad;
+  // permute: the dedicated decode kernel wants heads that are equal mod 8 in the same TMEM lane quarter (flame_decode.cuh)
+  const size_t arow = static_cast<size_t>(permute ? dec_phys_row(h) : h) * kKPad;
 
   float acc[15];
 #pragma unroll
@@ -787,6 +788,9 @@ struct dad3d_flame {
   float basis_scale = 1.f;
   __half* d_basis[2] = {nullptr, nullptr};   // [npad, kKPad] fp16 hi / lo planes of scale * [shapedirs | posedirs^T]
   float* d_w2 = nullptr;                     // [nv, 2] (sum of non-jaw weights, jaw weight) for the fused path
+  float* d_w2p = nullptr;                    // decode kernel: per vertex PAIR (w_rest v, w_rest v+1, w_jaw v, w_jaw v+1), whole tiles
+  __half* d_basis_dec = nullptr;             // decode kernel: hi plane with the rows of every 64-vertex tile regrouped per vertex
+                                             // pair as (x x' y y' z z') -- operands of the packed fp32 FMAs (flame_decode.cuh)
   bool jaw_only = false;                     // layout has no neck / eyeball pose -> fused epilogue is exact
   float* d_weights = nullptr;                // [nv, 5]
   float* d_jt = nullptr;                     // [15]
@@ -855,12 +859,13 @@ int launch_flame_decode(dad3d_flame* h, const __half* a_hi, int rows, const floa
                         float image_size, cudaStream_t stream) {
   int* configured = &h->smem_configured[kPair ? 3 : 2];
   if (!*configured) {
-    DAD3D_CUDA_OK(cudaFuncSetAttribute(flame_decode_kernel<kPair>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecSmemLimit));
+    DAD3D_CUDA_OK(cudaFuncSetAttribute(flame_decode_kernel<kPair, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecSmemLimit));
+    DAD3D_CUDA_OK(cudaFuncSetAttribute(flame_decode_kernel<kPair, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecSmemLimit));
     *configured = 1;
   }
   CUtensorMap map_a;
   {
-    const uint64_t dims[2] = {static_cast<uint64_t>(kKPad), static_cast<uint64_t>(rows)};
+    const uint64_t dims[2] = {static_cast<uint64_t>(kKPad), static_cast<uint64_t>(dec_rows_padded(rows))};
     const uint64_t strides[1] = {static_cast<uint64_t>(kKPad) * 2};
     const uint32_t box[2] = {kDecBlockK, kDecBlockM};
     if (!make_tmap_16bit(&map_a, a_hi, 2, dims, strides, box, nullptr)) return DAD3D_ERR_CUDA;
@@ -869,8 +874,8 @@ int launch_flame_decode(dad3d_flame* h, const __half* a_hi, int rows, const floa
   p.rows = rows;
   p.nv = h->nv;
   p.n_tiles = ceil_div(h->n3, kDecN);
-  const int m_tiles = ceil_div(rows, kDecBlockM);
-  p.m_units = kPair ? ceil_div(m_tiles, 2) : m_tiles;
+  const int m_tiles = dec_rows_padded(rows) / kDecBlockM;          // whole permutation blocks: two row tiles per 256 heads
+  p.m_units = kPair ? m_tiles / 2 : m_tiles;
   const int groups_max = decode_groups_max<kPair>(h);
   if (groups_max < 1) return DAD3D_ERR_CUDA;
   // fewer row tiles than SMs: split every row tile's sweep over the vertex tiles so that all SMs get work
@@ -889,7 +894,7 @@ int launch_flame_decode(dad3d_flame* h, const __half* a_hi, int rows, const floa
     p.stages = dec_max_stages<kPair>(kbs);
   }
   p.xf = xf;
-  p.w2 = h->d_w2;
+  p.w2 = h->d_w2p;
   p.verts3d = v3;
   p.proj = pj;
   p.pc = pc;
@@ -920,7 +925,7 @@ int launch_flame_decode(dad3d_flame* h, const __half* a_hi, int rows, const floa
     // diagnostics: the cycle-accounting instantiation, synchronous, table on stderr (never used by the product path)
     static bool configured[2] = {false, false};
     if (!configured[kPair ? 1 : 0]) {
-      DAD3D_CUDA_OK(cudaFuncSetAttribute(flame_decode_kernel<kPair, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecSmemLimit));
+      DAD3D_CUDA_OK(cudaFuncSetAttribute(flame_decode_kernel<kPair, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecSmemLimit));
       configured[kPair ? 1 : 0] = true;
     }
     const int nblk = static_cast<int>(cfg.gridDim.x);
@@ -929,7 +934,8 @@ int launch_flame_decode(dad3d_flame* h, const __half* a_hi, int rows, const floa
     DAD3D_CUDA_OK(cudaMalloc(&d_prof, words * sizeof(unsigned)));
     DAD3D_CUDA_OK(cudaMemsetAsync(d_prof, 0, words * sizeof(unsigned), stream));
     p.prof = d_prof;
-    DAD3D_CUDA_OK(cudaLaunchKernelEx(&cfg, flame_decode_kernel<kPair, true>, map_a, h->map_dec[kPair ? 1 : 0], p));
+    p.proj = nullptr;                                  // the profiled instantiation writes vertices only
+    DAD3D_CUDA_OK(cudaLaunchKernelEx(&cfg, flame_decode_kernel<kPair, true, false>, map_a, h->map_dec[kPair ? 1 : 0], p));
     count_launch();
     DAD3D_CUDA_OK(cudaStreamSynchronize(stream));
     std::vector<unsigned> hp(words);
@@ -950,13 +956,14 @@ int launch_flame_decode(dad3d_flame* h, const __half* a_hi, int rows, const floa
     std::fprintf(stderr,
                  "[decode profile] rows %d pair %d blocks %d stages %d kbs %d splits %d | cycles per CTA (mean)\n"
                  "  producer: total %.0f  wait_empty_slot %.0f  wait_tile_release %.0f\n"
-                 "  mma     : total %.0f  tiles %.1f  wait_free_accumulator %.0f  wait_full_slot %.0f  wait_coefficients %.0f\n"
+                 "  mma     : total %.0f  tiles %.1f  wait_free_accumulator %.0f  wait_full_slot %.0f  wait_coefficients %.0f (units 0/1/2: %.0f %.0f %.0f)\n"
                  "  epilogue: total %.0f  tiles %.1f  wait_full_accumulator %.0f  tmem_ld %.0f  math %.0f  stage+store %.0f (mean of 8 warps)\n",
                  rows, kPair ? 1 : 0, nblk, p.stages, p.kbs, p.splits, prod[7] / nb, prod[0] / nb, prod[1] / nb, mma[7] / nm, mma[6] / nm,
-                 mma[0] / nm, mma[1] / nm, mma[2] / nm, epi[7] / nb, epi[6] / nb, epi[0] / nb, epi[1] / nb, epi[2] / nb, epi[3] / nb);
+                 mma[0] / nm, mma[1] / nm, mma[2] / nm, mma[3] / nm, mma[4] / nm, mma[5] / nm, epi[7] / nb, epi[6] / nb, epi[0] / nb, epi[1] / nb, epi[2] / nb, epi[3] / nb);
     return DAD3D_OK;
   }
-  DAD3D_CUDA_OK(cudaLaunchKernelEx(&cfg, flame_decode_kernel<kPair>, map_a, h->map_dec[kPair ? 1 : 0], p));
+  if (pj) DAD3D_CUDA_OK(cudaLaunchKernelEx(&cfg, flame_decode_kernel<kPair, false, true>, map_a, h->map_dec[kPair ? 1 : 0], p));
+  else DAD3D_CUDA_OK(cudaLaunchKernelEx(&cfg, flame_decode_kernel<kPair, false, false>, map_a, h->map_dec[kPair ? 1 : 0], p));
   count_launch();
   DAD3D_CUDA_OK(cudaGetLastError());
   return DAD3D_OK;
@@ -968,7 +975,8 @@ template <>
 int decode_groups_max<true>(dad3d_flame* h) {
   if (h->max_clusters[1] == 0) {                       // co-resident CTA pairs (GPC packing may leave a few SMs unpaired)
     if (!h->smem_configured[3]) {
-      if (cudaFuncSetAttribute(flame_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecSmemLimit) != cudaSuccess)
+      if (cudaFuncSetAttribute(flame_decode_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecSmemLimit) != cudaSuccess ||
+          cudaFuncSetAttribute(flame_decode_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecSmemLimit) != cudaSuccess)
         return 0;
       h->smem_configured[3] = 1;
     }
@@ -984,7 +992,7 @@ int decode_groups_max<true>(dad3d_flame* h) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, flame_decode_kernel<true>, &cfg) != cudaSuccess || n < 1) {
+    if (cudaOccupancyMaxActiveClusters(&n, flame_decode_kernel<true, false, true>, &cfg) != cudaSuccess || n < 1) {
       set_error("no co-resident CTA pair fits");
       return 0;
     }
@@ -1140,6 +1148,27 @@ int dad3d_flame_create(dad3d_flame** out, const float* shapedirs_h, const float*
   const size_t plane = static_cast<size_t>(npad) * kKPad * sizeof(__half);
   CK(cudaMalloc(&h->d_basis[0], plane));
   CK(cudaMalloc(&h->d_basis[1], plane));
+  // decode-kernel copies: vertex-pair weight table and the pair-regrouped hi plane
+  const int dec_tiles = ceil_div(n3, kDecN);
+  std::vector<float> w2p(static_cast<size_t>(dec_tiles) * (kDecN / 3) * 2, 0.f);
+  std::vector<unsigned short> hi_dec(static_cast<size_t>(dec_tiles) * kDecN * kKPad, 0);
+  for (int t = 0; t < dec_tiles; ++t)
+    for (int j = 0; j < kDecN / 6; ++j) {                        // vertex pair j of tile t
+      const int v0 = t * (kDecN / 3) + 2 * j;
+      for (int e = 0; e < 2; ++e) {
+        const int v = v0 + e;
+        if (v >= n_vertices) continue;
+        w2p[(static_cast<size_t>(t) * (kDecN / 6) + j) * 4 + e] = w2[2 * v];
+        w2p[(static_cast<size_t>(t) * (kDecN / 6) + j) * 4 + 2 + e] = w2[2 * v + 1];
+        for (int c = 0; c < 3; ++c)
+          std::memcpy(&hi_dec[(static_cast<size_t>(t) * kDecN + 6 * j + 2 * c + e) * kKPad], &hi[(static_cast<size_t>(v) * 3 + c) * kKPad],
+                      kKPad * sizeof(unsigned short));
+      }
+    }
+  CK(cudaMalloc(&h->d_w2p, w2p.size() * sizeof(float)));
+  CK(cudaMalloc(&h->d_basis_dec, hi_dec.size() * sizeof(unsigned short)));
+  CK(cudaMemcpy(h->d_w2p, w2p.data(), w2p.size() * sizeof(float), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->d_basis_dec, hi_dec.data(), hi_dec.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
   CK(cudaMalloc(&h->d_w2, w2.size() * sizeof(float)));
   CK(cudaMalloc(&h->d_weights, static_cast<size_t>(n_vertices) * kJoints * sizeof(float)));
   CK(cudaMalloc(&h->d_jt, 15 * sizeof(float)));
@@ -1162,12 +1191,12 @@ int dad3d_flame_create(dad3d_flame** out, const float* shapedirs_h, const float*
     if (!make_tmap_16bit(&h->map_b48[p], h->d_basis[p], 2, dims, strides, box48, nullptr)) return fail(DAD3D_ERR_CUDA);
   }
   {
-    const uint64_t dims[2] = {static_cast<uint64_t>(kKPad), static_cast<uint64_t>(npad)};
+    const uint64_t dims[2] = {static_cast<uint64_t>(kKPad), static_cast<uint64_t>(ceil_div(n3, kDecN) * kDecN)};
     const uint64_t strides[1] = {static_cast<uint64_t>(kKPad) * 2};
     const uint32_t box192[2] = {kDecBlockK, kDecN};
     const uint32_t box96h[2] = {kDecBlockK, kDecN / 2};
-    if (!make_tmap_16bit(&h->map_dec[0], h->d_basis[0], 2, dims, strides, box192, nullptr)) return fail(DAD3D_ERR_CUDA);
-    if (!make_tmap_16bit(&h->map_dec[1], h->d_basis[0], 2, dims, strides, box96h, nullptr)) return fail(DAD3D_ERR_CUDA);
+    if (!make_tmap_16bit(&h->map_dec[0], h->d_basis_dec, 2, dims, strides, box192, nullptr)) return fail(DAD3D_ERR_CUDA);
+    if (!make_tmap_16bit(&h->map_dec[1], h->d_basis_dec, 2, dims, strides, box96h, nullptr)) return fail(DAD3D_ERR_CUDA);
   }
   h->fused_chunk = h->num_sms * kBlockM * 4;
   *out = h;
@@ -1179,6 +1208,8 @@ void dad3d_flame_destroy(dad3d_flame* h) {
   cudaFree(h->d_basis[0]);
   cudaFree(h->d_basis[1]);
   cudaFree(h->d_w2);
+  cudaFree(h->d_w2p);
+  cudaFree(h->d_basis_dec);
   cudaFree(h->d_weights);
   cudaFree(h->d_jt);
   cudaFree(h->d_jdirsT);
@@ -1190,7 +1221,8 @@ void dad3d_flame_destroy(dad3d_flame* h) {
 int32_t dad3d_flame_num_params(const dad3d_flame* h) { return h ? h->layout.n_params : 0; }
 int32_t dad3d_flame_num_vertices(const dad3d_flame* h) { return h ? h->nv : 0; }
 
-static size_t ws_coef_bytes(int rows) { return align_up(static_cast<size_t>(rows) * kKPad * sizeof(__half), 1024); }
+// coefficient rows: padded to whole 256-head permutation blocks (the dedicated decode kernel stores them permuted)
+static size_t ws_coef_bytes(int rows) { return align_up(static_cast<size_t>(dec_rows_padded(rows)) * kKPad * sizeof(__half), 1024); }
 static size_t ws_xf_bytes(int rows) { return align_up(static_cast<size_t>(rows) * kXfFloats * sizeof(float), 1024); }
 static size_t ws_vposed_bytes(const dad3d_flame* h, int rows) { return align_up(static_cast<size_t>(rows) * h->npad * sizeof(float), 1024); }
 
@@ -1241,7 +1273,7 @@ int dad3d_flame_decode(dad3d_flame* h, const float* params_d, int32_t B, int32_t
       const int threads = 256;
       const int blocks = ceil_div(rows * 32, threads);
       flame_prep_kernel<<<blocks, threads, 0, stream>>>(p, rows, h->layout, h->d_jt, h->d_jdirsT, flags, inv_scale, a_hi,
-                                                        a_lo, xf);
+                                                        a_lo, xf, dedicated ? 1 : 0);
       count_launch();
       DAD3D_CUDA_OK(cudaGetLastError());
     }
@@ -1391,7 +1423,7 @@ int dad3d_flame_backward(dad3d_flame* h, const float* params_d, int32_t B, int32
     const float* gp = grad_projected_d ? grad_projected_d + static_cast<size_t>(b0) * h->nv * pc : nullptr;
     float* gout = grad_params_d + static_cast<size_t>(b0) * h->layout.n_params;
     flame_prep_kernel<<<ceil_div(rows * 32, 256), 256, 0, stream>>>(p, rows, h->layout, h->d_jt, h->d_jdirsT, flags, inv_scale,
-                                                                     a_hi, a_lo, xf);
+                                                                     a_hi, a_lo, xf, 0);
     count_launch();
     DAD3D_CUDA_OK(cudaGetLastError());
     {   // forward blend product (recomputed): v_posed * basis_scale -> scratch

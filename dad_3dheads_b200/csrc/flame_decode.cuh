@@ -19,12 +19,27 @@
 //   * one tensor-core product per MAC (fp16 operands, 11-bit mantissa like TF32; the power-of-two pre-scaled basis keeps
 //     every operand normal).  Measured error of the vertices against the fp64 reference: relL2 1.5e-5, inside the 1e-4
 //     contract; the 3-product hi/lo mode (2e-7) remains available as DAD3D_BLEND_HILO through the tile engine.
-// Roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer (one elected lane), warps 2..9 epilogue -- warp w owns TMEM
-// lanes 32*(w%4).. (= heads) and column group (w-2)/4 (96 columns = 32 vertices), processed as 4 passes of 8 vertices:
-// TMEM -> registers -> skinning with two register-resident transforms per head and per-vertex (w_rest, w_jaw) broadcast
-// from a lane-distributed table (warp-uniform branches skip the jaw / rest transform where its weight is zero) -> per-warp
-// staging tile -> coalesced 128-byte global stores (the 60 276-byte row pitch of [B,5023,3] rules out TMA stores).
-// Two TMEM accumulator buffers (2 x 192 columns): the epilogue of tile i overlaps the MMAs of tile i+1.
+// Roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer (one elected lane), warps 2..9 epilogue.  Two TMEM accumulator
+// buffers (2 x 192 columns): the epilogue of tile i overlaps the MMAs of tile i+1.  Epilogue warp w owns TMEM lanes 32*(w%4)..
+// (= 32 heads) and one half of the tile's columns (96 columns = 32 vertices = 4 passes of 8 vertices); the two warps of a lane
+// quarter SWAP halves every tile.  Per pass: TMEM -> registers (the next pass's load is issued before this pass's stores) ->
+// skinning with packed fp32 FMAs (fma.rn.f32x2: the basis rows of a tile are regrouped per vertex pair as x x' y y' z z', so
+// accumulator columns arrive as register pairs; 24 FFMA2 per vertex pair instead of 48 FFMA), per-pair (w_rest, w_jaw) broadcast
+// from a per-warp shared-memory table -> 256-bit global stores straight from registers.  No staging buffer, no shuffles.
+//
+// Stores.  Rows of the reference layout [B,5023,3] are only 4-byte aligned (pitch 60 276 B), and a store that covers part of a
+// 32-byte sector costs the L2 a read-modify-write (measured: 24 M heads/s with runs cut at arbitrary offsets, 37 M with
+// sector-aligned runs).  Each lane therefore writes ITS OWN row: it keeps the last 8 floats of the previous pass (the carry) and
+// writes the window of 24 floats that starts c floats earlier, at the previous sector boundary, as three st.global.v8.f32
+// (STG.256, one whole sector each).  c = (address of the pass's first float, in floats) mod 8 is constant along a row (every
+// pass advances by 3 sectors) and depends on the head index only through head mod 8 (8 x pitch = 0 mod 8 floats), so the
+// coefficient rows are PERMUTED (dec_phys_row / dec_head_of: physical row tile 2b+t, lane quarter wq, lane l <-> head
+// 256 b + 8 l + 4 t + wq) to give all 32 lanes of a warp the same c: the window selection is a warp-uniform switch over c with
+// compile-time register choices.  Sector boundaries that fall between two warps' column ranges: at a tile boundary the carry
+// stays in the registers of the warp that swaps from half 1 to half 0; inside a tile, half 1 recomputes the two vertex pairs in
+// front of its range from the same accumulator (+6 % arithmetic).  Partial sectors remain only at the two ends of a unit's
+// column range (row start / row end).  Measured steps: staged scalar stores 36.7 M heads/s -> STG.256 per lane 36.6 (partial
+// sectors at every warp boundary: the L2's read-modify-write dominates) -> + FFMA2 38.9 -> whole sectors everywhere 41.0.
 #pragma once
 #include "ptx.cuh"
 
@@ -39,30 +54,39 @@ constexpr int kDecAResident = kDecKBlocks * kDecABytes;           // 112 KiB
 constexpr int kDecThreads = 320;
 constexpr int kDecEpiWarps = 8;
 constexpr int kDecPassCols = 24;                   // 8 vertices per pass
-constexpr int kDecCarry = 8;                       // floats of the previous pass kept in front of each staged row
-constexpr int kDecStagePitch = 36;                 // floats per staged row: 8 carry + 24 new + 4 pad (144 B: conflict-free STS.128)
-constexpr int kDecStageBytes = 32 * kDecStagePitch * 4;           // 3584 B per epilogue warp
+constexpr int kDecWarpCols = kDecN / 2;             // columns of a tile per epilogue warp (two column groups)
+constexpr int kDecPasses = kDecWarpCols / kDecPassCols;   // 4
+constexpr int kDecWtabBytes = 20 * 16;             // (w_rest, w_jaw) per vertex pair: the warp's 16 pairs of a tile + the 2 in front
 constexpr int kDecXfFloats = 68;
 constexpr int kDecSmemLimit = 227 * 1024;
+constexpr int kDecRowBlock = 256;                  // heads per permutation block (two row tiles)
+
+// physical coefficient row of head h, and its inverse for (row tile, lane quarter, lane)
+__host__ __device__ inline int dec_phys_row(int h) {
+  return (h & ~255) + ((h & 7) >> 2) * 128 + (h & 3) * 32 + ((h & 255) >> 3);
+}
+__host__ __device__ inline int dec_head_of(int m_tile, int wq, int lane) {
+  return (m_tile >> 1) * 256 + lane * 8 + (m_tile & 1) * 4 + wq;
+}
+__host__ __device__ inline int dec_rows_padded(int rows) { return (rows + kDecRowBlock - 1) / kDecRowBlock * kDecRowBlock; }
 
 struct DecodeParams {
-  int rows;                 // heads in this launch
+  int rows;                 // heads in this launch (coefficient rows are stored permuted: dec_phys_row; rows padded to 256)
   int nv;                   // vertices (5023)
   int n_tiles;              // ceil(3*nv / 192)
-  int m_units;              // row tiles (non-pair) or row-tile pairs (pair)
+  int m_units;              // row tiles (non-pair) or row-tile pairs (pair); always whole 256-head blocks
   int splits;               // each m unit is split into `splits` contiguous ranges of vertex tiles
   int stages;               // depth of the basis ring (slots)
   int kbs;                  // k-blocks per ring slot (1..4): one full/empty barrier round trip per slot
   const float* xf;          // [rows][68] per-head transform records (flame_prep_kernel)
-  const float* w2;          // [nv][2] (w_rest, w_jaw)
+  const float* w2;          // [n_tiles * 64][2] (w_rest, w_jaw), zero-padded past nv
   float* verts3d;           // [rows][nv][3] or null
   float* proj;              // [rows][nv][pc] or null
   int pc;
   float image_size;
   int poll;                 // 1: producer / MMA warps poll their barriers with test_wait instead of try_wait (A/B)
   unsigned* prof;           // kProf instantiation only (DAD3D_DECODE_PROFILE): [block][10 warps][8] cycle counters
-  int debug;                // diagnostics only (DAD3D_DECODE_DEBUG): 1 = all global stores go to the first 128 rows (L2-resident
-                            // footprint: isolates the SM -> L2 store path from DRAM), 2 = stores predicated off at run time, 3 = the epilogue only
+  int debug;                // diagnostics only (DAD3D_DECODE_DEBUG): 2 = stores predicated off at run time, 3 = the epilogue only
                             // hands the accumulator back (pure main-loop rate)
 };
 
@@ -70,13 +94,13 @@ template <bool kPair>
 __host__ __device__ inline int dec_b_stage_bytes() { return (kPair ? kDecN / 2 : kDecN) * kDecBlockK * 2; }
 template <bool kPair>
 __host__ inline int dec_max_stages(int kbs) {
-  const int fixed = kDecAResident + kDecEpiWarps * kDecStageBytes + 1024 + 512;
+  const int fixed = kDecAResident + kDecEpiWarps * kDecWtabBytes + 1024 + 512;
   int s = (kDecSmemLimit - fixed) / (kbs * dec_b_stage_bytes<kPair>());
   return s > 8 ? 8 : s;
 }
 template <bool kPair>
 __host__ inline int dec_smem_bytes(int stages, int kbs) {
-  return kDecAResident + stages * kbs * dec_b_stage_bytes<kPair>() + kDecEpiWarps * kDecStageBytes + 1024 + 512;
+  return kDecAResident + stages * kbs * dec_b_stage_bytes<kPair>() + kDecEpiWarps * kDecWtabBytes + 1024 + 512;
 }
 
 // unit u of this CTA (pair): row tile (pair) m, vertex tiles [n0, n1)
@@ -90,85 +114,58 @@ __device__ __forceinline__ bool dec_unit_at(const DecodeParams& p, int group, in
   return true;
 }
 
-// ---- sector-aligned stores.  Rows of the reference layout are only 4-byte aligned (pitch 60 276 B), and a store that covers
-// part of a 32-byte sector costs the L2 a read-modify-write (measured: 24.4 M heads/s with runs cut at arbitrary offsets,
-// 37.3 M with sector-aligned runs).  Each staged row therefore keeps the last 8 floats of the previous pass in front of the
-// 24 new ones (staged positions [0,8) | [8,32)), and row r is written as the window of 24 floats that starts
-// c_r = (address of the pass's first float of row r, in floats) mod 8 floats EARLIER: 3 whole, aligned sectors.  c_r depends
-// on the row only (every pass advances a row by exactly 3 sectors).  The first pass of a warp's column range has no carry
-// (head elements are predicated off: one partial sector per 96 columns), the last pass also writes the c_r-float tail.
-//
-// Hot path: columns [0,16) of the window leave as 16 warp stores of 2 rows x 16 floats, columns [16,24) as 8 warp stores of
-// 4 rows x 8 floats; shared-memory loads are issued eight at a time ahead of the global stores they feed.  `cb` = (address
-// of row 0's first new float, in floats) mod 8, `rho` = row pitch mod 8.
+// ---- window stores.  ext = carry[8] ++ x[RUN] are the floats [g0 - 8, g0 + RUN) of this lane's row (g0 = the pass's first float);
+// the window [g0 - C, g0 - C + RUN) = ext[8 - C, 8 - C + RUN) starts on a sector boundary and leaves as RUN/8 whole-sector
+// stores.  `head`: no valid carry (first pass of the warp's column range) -- the first sector is partial and its own 8 - C floats
+// go out as scalar stores; `tail`: last pass of the range -- the C floats behind the window follow as scalar stores.
+template <int RUN, int C>
+__device__ __forceinline__ void dec_store_c(float* __restrict__ dst, const float (&carry)[8], const float (&x)[RUN], bool head,
+                                            bool tail) {
+#define DEC_EXT(e) ((e) < 8 ? carry[(e) < 8 ? (e) : 0] : x[(e) >= 8 ? (e) - 8 : 0])
+  float* w = dst - C;
+  if (C == 0 || !head) {
+    ptx::st_global_v8(w, DEC_EXT(8 - C), DEC_EXT(9 - C), DEC_EXT(10 - C), DEC_EXT(11 - C), DEC_EXT(12 - C), DEC_EXT(13 - C),
+                      DEC_EXT(14 - C), DEC_EXT(15 - C));
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8 - C; ++j) dst[j] = x[j];
+  }
+#pragma unroll
+  for (int k = 1; k < RUN / 8; ++k)
+    ptx::st_global_v8(w + 8 * k, DEC_EXT(8 - C + 8 * k), DEC_EXT(9 - C + 8 * k), DEC_EXT(10 - C + 8 * k), DEC_EXT(11 - C + 8 * k),
+                      DEC_EXT(12 - C + 8 * k), DEC_EXT(13 - C + 8 * k), DEC_EXT(14 - C + 8 * k), DEC_EXT(15 - C + 8 * k));
+  if (C > 0 && tail) {
+#pragma unroll
+    for (int j = 0; j < C; ++j) dst[RUN - C + j] = x[RUN - C + j];
+  }
+#undef DEC_EXT
+}
 template <int RUN>
-__device__ __forceinline__ void dec_flush_aligned(float* __restrict__ dst, unsigned pitch, const float* __restrict__ stage, int lane,
-                                                  unsigned cb, unsigned rho, bool head, bool tail) {
-  const int off_min = head ? 0 : -kDecCarry;          // first pass of a column range: nothing in front of the new floats
-  // c_r = (cb + rho r) mod 8 depends on r mod 8 only (8 rho = 0 mod 8): a lane meets 4 row residues in the first part and 2
-  // in each of the others, so the shifts, shared-memory bases, row pointers and head predicates are set up once per flush
-  {
-    const int rl = (lane >> 4) * 4, c0 = lane & 15;    // rows rl + {0..3, 8..11, 16..19, 24..27}, 16 columns per row
-    const float* sp[4];
-    float* gp[4];
-    bool ok[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int off = c0 - static_cast<int>((cb + rho * (rl + k)) & 7u);
-      sp[k] = stage + (rl + k) * kDecStagePitch + kDecCarry + off;
-      gp[k] = dst + static_cast<size_t>(rl + k) * pitch + off;
-      ok[k] = off >= off_min;
-    }
-    const size_t step8 = static_cast<size_t>(pitch) * 8;
-#pragma unroll
-    for (int g = 0; g < 4; g += 2) {
-      float t[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) t[u] = sp[u & 3][(g + (u >> 2)) * 8 * kDecStagePitch];
-#pragma unroll
-      for (int u = 0; u < 8; ++u)
-        if (ok[u & 3]) gp[u & 3][(g + (u >> 2)) * step8] = t[u];
-    }
-  }
-  if (RUN > 16) {
-    const int rl = (lane >> 3) * 2, c0 = 16 + (lane & 7);   // rows rl + {0,1, 8,9, 16,17, 24,25}, columns [16,24)
-    const float* sp[2];
-    float* gp[2];
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int off = c0 - static_cast<int>((cb + rho * (rl + k)) & 7u);
-      sp[k] = stage + (rl + k) * kDecStagePitch + kDecCarry + off;
-      gp[k] = dst + static_cast<size_t>(rl + k) * pitch + off;
-    }
-    const size_t step8 = static_cast<size_t>(pitch) * 8;
-    float t[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) t[u] = sp[u & 1][(u >> 1) * 8 * kDecStagePitch];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) gp[u & 1][(u >> 1) * step8] = t[u];
-  }
-  if (tail) {                                          // the last c_r floats of the warp's column range (c_r < 8): 4 rows per store
-    const int rl = lane >> 3, k8 = lane & 7;           // rows rl + 4 u: residues rl and rl + 4
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int c = static_cast<int>((cb + rho * (rl + 4 * k)) & 7u);
-      if (k8 < c) {
-        const float* sp = stage + (rl + 4 * k) * kDecStagePitch + kDecCarry + RUN - c + k8;
-        float* gp = dst + static_cast<size_t>(rl + 4 * k) * pitch + RUN - c + k8;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) gp[static_cast<size_t>(u) * 8 * pitch] = sp[u * 8 * kDecStagePitch];
-      }
-    }
+__device__ __forceinline__ void dec_store(float* __restrict__ dst, unsigned c, const float (&carry)[8], const float (&x)[RUN],
+                                          bool head, bool tail) {
+  switch (c) {                                         // warp-uniform
+    case 0: dec_store_c<RUN, 0>(dst, carry, x, head, tail); break;
+    case 1: dec_store_c<RUN, 1>(dst, carry, x, head, tail); break;
+    case 2: dec_store_c<RUN, 2>(dst, carry, x, head, tail); break;
+    case 3: dec_store_c<RUN, 3>(dst, carry, x, head, tail); break;
+    case 4: dec_store_c<RUN, 4>(dst, carry, x, head, tail); break;
+    case 5: dec_store_c<RUN, 5>(dst, carry, x, head, tail); break;
+    case 6: dec_store_c<RUN, 6>(dst, carry, x, head, tail); break;
+    default: dec_store_c<RUN, 7>(dst, carry, x, head, tail); break;
   }
 }
-// Edge tiles (last row tile of the batch, last vertex tile of the mesh): plain predicated loop, one row per warp store, no
-// carry (the staged new floats [8, 8 + RUN) of each row go out as they are).
+// Last, partly valid pass of a row (the mesh ends inside it): the carried floats in front of it, then the valid new ones.
 template <int RUN>
-__device__ __noinline__ void dec_flush_edge(float* __restrict__ dst, unsigned pitch, const float* __restrict__ stage, int lane,
-                                            int rows_valid, int cols_valid) {
-  if (lane < cols_valid && lane < RUN)
-    for (int r = 0; r < rows_valid && r < 32; ++r)
-      dst[static_cast<size_t>(r) * pitch + lane] = stage[r * kDecStagePitch + kDecCarry + lane];
+__device__ __forceinline__ void dec_store_edge(float* __restrict__ dst, unsigned c, const float (&carry)[8], const float (&x)[RUN],
+                                            bool head, int nvalid) {
+  if (!head) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j >= 8 - static_cast<int>(c)) dst[j - 8] = carry[j];
+  }
+#pragma unroll
+  for (int j = 0; j < RUN; ++j)
+    if (j < nvalid) dst[j] = x[j];
 }
 
 __device__ __forceinline__ void dec_wait(uint64_t* bar, uint32_t parity, int poll) {
@@ -181,8 +178,9 @@ __device__ __forceinline__ void dec_wait(uint64_t* bar, uint32_t parity, int pol
 //   MMA       [0] waiting for a free accumulator (epilogue back-pressure), [1] waiting for a full ring slot (feed starvation),
 //             [2] waiting for the coefficient tile, [6] tiles, [7] whole role
 //   epilogue  [0] waiting for a full accumulator, [1] TMEM loads, [2] skinning math, [3] staging + stores, [6] tiles, [7] whole role
-template <bool kPair, bool kProf = false>
-__global__ void __launch_bounds__(kDecThreads, 1)
+// kProj: the projected output is requested too (its carry and constants cost ~12 registers: own instantiation)
+template <bool kPair, bool kProf = false, bool kProj = true>
+__global__ void __launch_bounds__(kDecThreads, 1)   // registers are allocated per 4 warps: 320 threads count as 384 -> 168 / thread
 flame_decode_kernel(const __grid_constant__ CUtensorMap map_a,     // coefficients [rows, 448] fp16, box 64 x 128
                     const __grid_constant__ CUtensorMap map_b,     // basis [npad, 448] fp16, box 64 x (192 | 96)
                     const DecodeParams p) {
@@ -192,8 +190,8 @@ flame_decode_kernel(const __grid_constant__ CUtensorMap map_a,     // coefficien
   const int kBStage = p.kbs * kBBlock;                             // one ring slot = p.kbs k-blocks
   uint8_t* smem_a = smem;                                          // [7][16 KiB] resident coefficient tile
   uint8_t* smem_b = smem + kDecAResident;                          // [stages][kBStage]
-  uint8_t* stage_out = smem_b + p.stages * kBStage;                // [8][3584 B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_out + kDecEpiWarps * kDecStageBytes);
+  uint8_t* wtab_all = smem_b + p.stages * kBStage;                 // [8][512 B] per-warp (w_rest, w_jaw) table of the current tile
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wtab_all + kDecEpiWarps * kDecWtabBytes);
   uint64_t* full_bar = bars;                  // [8]  basis ring
   uint64_t* empty_bar = bars + 8;             // [8]
   uint64_t* afull_bar = bars + 16;            // [7]  one per k-block of the resident coefficient tile
@@ -221,7 +219,7 @@ flame_decode_kernel(const __grid_constant__ CUtensorMap map_a,     // coefficien
     ptx::mbar_init(aempty_bar, 1);
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(&tfull_bar[b], 1);
-      ptx::mbar_init(&tempty_bar[b], (kPair ? 2 : 1) * kDecEpiWarps * 32);   // pair: both CTAs' epilogues release the leader's
+      ptx::mbar_init(&tempty_bar[b], (kPair ? 2 : 1) * kDecEpiWarps);   // one arrive per epilogue warp (pair: both CTAs')
     }
     ptx::fence_mbar_init();
   }
@@ -304,7 +302,7 @@ flame_decode_kernel(const __grid_constant__ CUtensorMap map_a,     // coefficien
       int acc = 0;
       uint32_t acc_phase = 0;
       int m, n0, n1;
-      unsigned mc0 = 0, mc1 = 0, mc2 = 0, mt0 = 0, mtiles = 0, mstart = 0;
+      unsigned mc0 = 0, mc1 = 0, mc2 = 0, mt0 = 0, mtiles = 0, mstart = 0, mu0 = 0, mu1 = 0, mu2 = 0;
       if constexpr (kProf) mstart = clock();
       for (int ui = 0; dec_unit_at(p, group, n_groups, ui, &m, &n0, &n1); ++ui) {
         for (int n = n0; n < n1; ++n) {
@@ -354,183 +352,212 @@ flame_decode_kernel(const __grid_constant__ CUtensorMap map_a,     // coefficien
           if (acc == 0) acc_phase ^= 1u;
         }
         aphase ^= 1u;
+        if constexpr (kProf) {                       // coefficient wait of the first three units separately
+          if (ui == 0) mu0 = mc2;
+          if (ui == 1) mu1 = mc2 - mu0;
+          if (ui == 2) mu2 = mc2 - mu0 - mu1;
+        }
       }
       if constexpr (kProf) {
         if (lane == 0) {
           unsigned* o = p.prof + (static_cast<size_t>(blockIdx.x) * 10 + 1) * 8;
-          o[0] = mc0; o[1] = mc1; o[2] = mc2; o[6] = mtiles; o[7] = clock() - mstart;
+          o[0] = mc0; o[1] = mc1; o[2] = mc2; o[3] = mu0; o[4] = mu1; o[5] = mu2; o[6] = mtiles; o[7] = clock() - mstart;
         }
       }
     }
   } else {
     // ===================================================== epilogue warps
     const int wq = warp & 3;                       // TMEM lane quarter
-    const int grp = (warp - 2) >> 2;               // column group: columns [96 grp, 96 grp + 96) of the tile
-    float* stage = reinterpret_cast<float*>(stage_out + (warp - 2) * kDecStageBytes);
-    float4* srow = reinterpret_cast<float4*>(stage + lane * kDecStagePitch);
-    const uint32_t tempty_cluster0 = kPair ? ptx::mapa_u32(&tempty_bar[0], 0) : 0u;
-    const uint32_t tempty_cluster1 = kPair ? ptx::mapa_u32(&tempty_bar[1], 0) : 0u;
-    int acc = 0;
+    const int grp = (warp - 2) >> 2;               // epilogue group = accumulator buffer: tiles with (tile counter & 1) == grp
+    float4* wtab = reinterpret_cast<float4*>(wtab_all + (warp - 2) * kDecWtabBytes);
+    const uint32_t tempty_remote0 = kPair ? ptx::mapa_u32(&tempty_bar[0], 0) : 0u;
+    const uint32_t tempty_remote1 = kPair ? ptx::mapa_u32(&tempty_bar[1], 0) : 0u;
+    int acc = 0;                                   // accumulator buffer of the current tile: alternates per tile, across units too
     uint32_t acc_phase = 0;
-    float R[12], Jw[12], cx = 0.f, cy = 0.f, cz = 0.f, sc = 1.f, tx = 0.f, ty = 0.f;
+    float2 R2[12], J2[12], c2x, c2y, c2z;          // per-head transforms and offset, both halves equal (operands of the packed FMAs)
+    float sc = 1.f, tx = 0.f, ty = 0.f;
     int m, n0, n1;
     const int nv3 = p.nv * 3;
-    const int nv3s = p.debug == 4 ? ((nv3 + 7) & ~7) : nv3;      // debug 4: sector-aligned row pitch (timing experiment only)
     const int pc = p.pc;
     const float hs = 0.5f * p.image_size;
-    const unsigned rho_v = static_cast<unsigned>(nv3s) & 7u, rho_q = static_cast<unsigned>(p.nv * pc) & 7u;   // row pitch mod 8 floats
-    float vprev[8], qprev[8];                      // this row's last 8 floats of the previous pass (the carry), per output
+    float vcar[8], qcar[8];                        // this row's last 8 floats of the previous pass (the carry), per output
 #pragma unroll
-    for (int j = 0; j < 8; ++j) vprev[j] = qprev[j] = 0.f;
+    for (int j = 0; j < 8; ++j) vcar[j] = qcar[j] = 0.f;
     unsigned ec0 = 0, ec1 = 0, ec2 = 0, ec3 = 0, et0 = 0, etiles = 0, estart = 0;
     if constexpr (kProf) estart = clock();
+    const uint32_t t_wq = tmem_base + (static_cast<uint32_t>(wq * 32) << 16);
     for (int ui = 0; dec_unit_at(p, group, n_groups, ui, &m, &n0, &n1); ++ui) {
-      const int head0 = (kPair ? 2 * m + crank : m) * kDecBlockM + wq * 32;
+      const int head = dec_head_of(kPair ? 2 * m + crank : m, wq, lane);
+      const bool row_ok = head < p.rows && p.debug != 2;
       {   // per-head transforms -> registers, once per unit (rows past the batch read the last valid record; never stored)
-        const int h = min(head0 + lane, p.rows - 1);
+        const int h = min(head, p.rows - 1);
         const float4* src = reinterpret_cast<const float4*>(p.xf + static_cast<size_t>(h) * kDecXfFloats);
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
           const float4 a = __ldg(&src[q]);           // joint 0 (rest)
           const float4 b = __ldg(&src[6 + q]);       // joint 2 (jaw)
-          R[4 * q] = a.x; R[4 * q + 1] = a.y; R[4 * q + 2] = a.z; R[4 * q + 3] = a.w;
-          Jw[4 * q] = b.x; Jw[4 * q + 1] = b.y; Jw[4 * q + 2] = b.z; Jw[4 * q + 3] = b.w;
+          R2[4 * q] = make_float2(a.x, a.x); R2[4 * q + 1] = make_float2(a.y, a.y);
+          R2[4 * q + 2] = make_float2(a.z, a.z); R2[4 * q + 3] = make_float2(a.w, a.w);
+          J2[4 * q] = make_float2(b.x, b.x); J2[4 * q + 1] = make_float2(b.y, b.y);
+          J2[4 * q + 2] = make_float2(b.z, b.z); J2[4 * q + 3] = make_float2(b.w, b.w);
         }
         const float4 u = __ldg(&src[15]);
         const float4 w = __ldg(&src[16]);
-        cx = u.x; cy = u.y; cz = u.z; sc = u.w; tx = w.x; ty = w.y;
+        c2x = make_float2(u.x, u.x); c2y = make_float2(u.y, u.y); c2z = make_float2(u.z, u.z);
+        sc = u.w; tx = w.x; ty = w.y;
       }
-      const int rows_left = (p.debug == 4 ? p.rows - 32 : p.rows) - head0;   // rows of this warp inside the batch (<= 0: nothing to store)
-      const int head_store = p.debug == 1 ? (head0 & 127) : head0;
-      float* const v_base = p.verts3d ? p.verts3d + static_cast<size_t>(head_store) * nv3s : nullptr;
-      float* const q_base = p.proj ? p.proj + static_cast<size_t>(head_store) * p.nv * pc : nullptr;
-      // (w_rest, w_jaw) of the warp's 32 vertices of a tile: lane l holds floats 2*vertex+{0,1} of vertices l/2 and 16+l/2
-      int vb = n0 * (kDecN / 3) + grp * 32;
-      float wl0 = (vb * 2 + lane < p.nv * 2) ? __ldg(&p.w2[vb * 2 + lane]) : 0.f;
-      float wl1 = (vb * 2 + 32 + lane < p.nv * 2) ? __ldg(&p.w2[vb * 2 + 32 + lane]) : 0.f;
-      for (int n = n0; n < n1; ++n) {
-        const float wc0 = wl0, wc1 = wl1;
-        if (n + 1 < n1) {                            // next tile's table: the L2 latency hides behind this tile's work
-          const int vn = vb + kDecN / 3;
-          wl0 = (vn * 2 + lane < p.nv * 2) ? __ldg(&p.w2[vn * 2 + lane]) : 0.f;
-          wl1 = (vn * 2 + 32 + lane < p.nv * 2) ? __ldg(&p.w2[vn * 2 + 32 + lane]) : 0.f;
-        }
-        // sector phase of the tile's first float of row 0 of this warp (in floats, mod 8), for both outputs
-        const bool tile_full = rows_left >= 32 && (vb + 32) * 3 <= nv3;
-        const unsigned cb_v = v_base ? static_cast<unsigned>((reinterpret_cast<uintptr_t>(v_base + vb * 3) >> 2) & 7u) : 0u;
-        const unsigned cb_q = q_base ? static_cast<unsigned>((reinterpret_cast<uintptr_t>(q_base + vb * pc) >> 2) & 7u) : 0u;
+      float* const v_row = p.verts3d ? p.verts3d + static_cast<size_t>(min(head, p.rows - 1)) * nv3 : nullptr;
+      float* const q_row = (kProj && p.proj) ? p.proj + static_cast<size_t>(min(head, p.rows - 1)) * p.nv * pc : nullptr;
+      // sector phase of the row (floats mod 8): the same for all lanes of the warp (heads = const mod 8), constant along the row
+      const unsigned c_v = __shfl_sync(0xffffffffu, static_cast<unsigned>((reinterpret_cast<uintptr_t>(v_row) >> 2) & 7u), 0);
+      const unsigned c_q = __shfl_sync(0xffffffffu, static_cast<unsigned>((reinterpret_cast<uintptr_t>(q_row) >> 2) & 7u), 0);
+      for (int n = n0; n < n1; ++n, acc ^= 1, acc_phase ^= (acc == 0 ? 1u : 0u)) {
+        // Column half of this warp: the two warps of a lane quarter SWAP halves every tile, so the warp that ends tile n (half 1)
+        // begins tile n+1 (half 0) and the carry across the tile boundary stays in its registers.  Half 1 begins inside the tile:
+        // it recomputes the two vertex pairs in front of its range from the same accumulator (12 more columns, +6 % arithmetic)
+        // to get its carry.  With that every sector inside a unit's column range is written whole, by one lane.
+        const int half = grp ^ (n & 1);
+        const uint32_t t_lane = t_wq + static_cast<uint32_t>(acc * kDecN + half * kDecWarpCols);
+        const uint32_t tempty_remote = acc ? tempty_remote1 : tempty_remote0;
+        // (w_rest, w_jaw) per vertex pair -- pairs [14 half, 14 half + 18) of the tile: entries 0, 1 are the two pairs in front of
+        // half 1 (unused by half 0), entries 2.. the warp's own 16.  The L2 latency hides behind the wait for the accumulator.
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(p.w2) + static_cast<size_t>(n) * (kDecN / 6) +
+                                min(max(16 * half - 2 + lane, 0), kDecN / 6 - 1));
+        const int col_t = n * kDecN + half * kDecWarpCols;   // first float of the warp's column range within a row
         if constexpr (kProf) et0 = clock();
         ptx::mbar_wait(&tfull_bar[acc], acc_phase);
         if constexpr (kProf) { ec0 += clock() - et0; ++etiles; }
         ptx::tc_fence_after();
-        const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + static_cast<uint32_t>(acc * kDecN + grp * 96);
         if (p.debug == 3) {
           ptx::tc_fence_before();
-          if constexpr (kPair) ptx::mbar_arrive_cluster(acc ? tempty_cluster1 : tempty_cluster0);
-          else ptx::mbar_arrive(&tempty_bar[acc]);
-        }
-#pragma unroll 1
-        for (int q = 0; q < 4 && p.debug != 3; ++q) {          // 4 passes of 8 vertices (24 accumulator columns)
-          float xa[24];
-          if constexpr (kProf) et0 = clock();
-          ptx::tmem_ld_32x32b_x16_f(t_acc + q * 24, xa);
-          ptx::tmem_ld_32x32b_x8_f(t_acc + q * 24 + 16, xa + 16);
-          ptx::tmem_ld_wait();
-          if constexpr (kProf) { const unsigned t = clock(); ec1 += t - et0; et0 = t; }
-          if (q == 3) {                              // the warp's share of the accumulator has been read: hand TMEM back
-            ptx::tc_fence_before();
-            if constexpr (kPair) ptx::mbar_arrive_cluster(acc ? tempty_cluster1 : tempty_cluster0);
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (kPair) ptx::mbar_arrive_cluster(tempty_remote);
             else ptx::mbar_arrive(&tempty_bar[acc]);
           }
-          const float wl = (q & 2) ? wc1 : wc0;
-          const int lsel = (q & 1) * 16;
+          continue;
+        }
+        // Skinning of one vertex pair with packed fp32 FMAs (fma.rn.f32x2): the basis rows of a tile are regrouped per vertex
+        // pair as (x x' y y' z z'), so the accumulator columns arrive as ready-made register pairs; the per-head constants are
+        // held duplicated.  24 FFMA2 per vertex pair instead of 48 FFMA -- the epilogue is issue-bound.
+        auto skin_pair = [&](const float* a6, const float4& w4, float* o6) {
+          const float2 wr = make_float2(w4.x, w4.y), wj = make_float2(w4.z, w4.w);   // (w_rest v, w_rest v'), (w_jaw v, w_jaw v')
+          const float2 px = make_float2(a6[0], a6[1]), py = make_float2(a6[2], a6[3]), pz = make_float2(a6[4], a6[5]);
+          const float2 rx = __ffma2_rn(R2[0], px, __ffma2_rn(R2[1], py, __ffma2_rn(R2[2], pz, R2[3])));
+          const float2 ry = __ffma2_rn(R2[4], px, __ffma2_rn(R2[5], py, __ffma2_rn(R2[6], pz, R2[7])));
+          const float2 rz = __ffma2_rn(R2[8], px, __ffma2_rn(R2[9], py, __ffma2_rn(R2[10], pz, R2[11])));
+          const float2 jx = __ffma2_rn(J2[0], px, __ffma2_rn(J2[1], py, __ffma2_rn(J2[2], pz, J2[3])));
+          const float2 jy = __ffma2_rn(J2[4], px, __ffma2_rn(J2[5], py, __ffma2_rn(J2[6], pz, J2[7])));
+          const float2 jz = __ffma2_rn(J2[8], px, __ffma2_rn(J2[9], py, __ffma2_rn(J2[10], pz, J2[11])));
+          const float2 ox = __ffma2_rn(wj, jx, __ffma2_rn(wr, rx, c2x));
+          const float2 oy = __ffma2_rn(wj, jy, __ffma2_rn(wr, ry, c2y));
+          const float2 oz = __ffma2_rn(wj, jz, __ffma2_rn(wr, rz, c2z));
+          o6[0] = ox.x; o6[1] = oy.x; o6[2] = oz.x;
+          o6[3] = ox.y; o6[4] = oy.y; o6[5] = oz.y;
+        };
+        // (Issuing the load of pass q+1 before the arithmetic of pass q, into a second register buffer, was measured: the wait for
+        // the columns shrinks from ~400 to ~100 cycles per pass but the time reappears in the stores -- the store path is the
+        // bottleneck -- and the kernel gets 4 % slower.)
+        float xa[24];
+        if constexpr (kProf) et0 = clock();
+        float xb[16];
+        if (half) ptx::tmem_ld_32x32b_x16_f(t_lane - 16, xb);      // the 12 columns in front of half 1 (4 more ride along)
+        ptx::tmem_ld_32x32b_x16_f(t_lane, xa);
+        ptx::tmem_ld_32x32b_x8_f(t_lane + 16, xa + 16);
+        __syncwarp();                                // the previous tile's table reads are done
+        if (lane < 18) wtab[lane] = wv;
+        __syncwarp();
+        if (half) {                                  // carry of half 1: the last 8 floats in front of column 96 of the tile
+          ptx::tmem_ld_wait_16(xb);
+          float xpre[12];
+          skin_pair(xb + 4, wtab[0], xpre);
+          skin_pair(xb + 10, wtab[1], xpre + 6);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) vcar[j] = xpre[4 + j];
+          if constexpr (kProj) {
+            if (pc == 2) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                qcar[2 * i] = ((xpre[3 * i] * sc + tx) + 1.0f) * hs;
+                qcar[2 * i + 1] = ((xpre[3 * i + 1] * sc + ty) + 1.0f) * hs;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int e = 4 + j;                 // float e of the 12: coordinate e % 3
+                qcar[j] = ((xpre[e] * sc + (e % 3 == 0 ? tx : e % 3 == 1 ? ty : 0.0f)) + 1.0f) * hs;
+              }
+            }
+          }
+        }
+#pragma unroll 1
+        for (int q = 0; q < kDecPasses; ++q) {       // 4 passes of 8 vertices (24 accumulator columns)
+          ptx::tmem_ld_wait_24(xa);
+          if constexpr (kProf) { const unsigned t = clock(); ec1 += t - et0; et0 = t; }
           float x[24];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float px = xa[3 * i], py = xa[3 * i + 1], pz = xa[3 * i + 2];
-            const float wr = __shfl_sync(0xffffffffu, wl, lsel + 2 * i);
-            const float wj = __shfl_sync(0xffffffffu, wl, lsel + 2 * i + 1);
-            const float rx = fmaf(R[0], px, fmaf(R[1], py, fmaf(R[2], pz, R[3])));
-            const float ry = fmaf(R[4], px, fmaf(R[5], py, fmaf(R[6], pz, R[7])));
-            const float rz = fmaf(R[8], px, fmaf(R[9], py, fmaf(R[10], pz, R[11])));
-            const float jx = fmaf(Jw[0], px, fmaf(Jw[1], py, fmaf(Jw[2], pz, Jw[3])));
-            const float jy = fmaf(Jw[4], px, fmaf(Jw[5], py, fmaf(Jw[6], pz, Jw[7])));
-            const float jz = fmaf(Jw[8], px, fmaf(Jw[9], py, fmaf(Jw[10], pz, Jw[11])));
-            x[3 * i] = fmaf(wj, jx, fmaf(wr, rx, cx));
-            x[3 * i + 1] = fmaf(wj, jy, fmaf(wr, ry, cy));
-            x[3 * i + 2] = fmaf(wj, jz, fmaf(wr, rz, cz));
-          }
-          const int vfirst = vb + q * 8;
-          const int ncols = min(kDecPassCols, nv3 - vfirst * 3);        // valid floats of this pass's run (<= 0: past the mesh)
-          if constexpr (kProf) {
-            // pin the math in front of the second clock read: the staged values depend on it
-            float sink = 0.f;
-#pragma unroll
-            for (int j = 0; j < 24; ++j) sink += x[j];
-            if (sink == 1.2345e-33f) ec2 += 1u;
-            const unsigned t = clock(); ec2 += t - et0; et0 = t;
-          }
-          if (ncols <= 0 || rows_left <= 0 || p.debug == 2) continue;
-          if (v_base) {
-            // staged row = [8 carry floats of the previous pass | 24 new floats]
-            srow[0] = make_float4(vprev[0], vprev[1], vprev[2], vprev[3]);
-            srow[1] = make_float4(vprev[4], vprev[5], vprev[6], vprev[7]);
-#pragma unroll
-            for (int j = 0; j < 6; ++j) srow[2 + j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) vprev[j] = x[16 + j];
+          for (int i = 0; i < 4; ++i) skin_pair(xa + 6 * i, wtab[2 + 4 * q + i], x + 6 * i);
+          if (q + 1 < kDecPasses) {                  // next pass's accumulator columns: in flight behind this pass's stores
+            ptx::tmem_ld_32x32b_x16_f(t_lane + (q + 1) * kDecPassCols, xa);
+            ptx::tmem_ld_32x32b_x8_f(t_lane + (q + 1) * kDecPassCols + 16, xa + 16);
+          } else {                                   // the warp's share of the accumulator has been read: hand the buffer back
+            ptx::tc_fence_before();
             __syncwarp();
-            float* dst = v_base + vfirst * 3;
-            if (tile_full) dec_flush_aligned<24>(dst, static_cast<unsigned>(nv3s), stage, lane, (cb_v + 24u * q) & 7u, rho_v, q == 0, q == 3);
-            else dec_flush_edge<24>(dst, static_cast<unsigned>(nv3s), stage, lane, rows_left, ncols);
-            __syncwarp();
+            if (lane == 0) {
+              if constexpr (kPair) ptx::mbar_arrive_cluster(tempty_remote);
+              else ptx::mbar_arrive(&tempty_bar[acc]);
+            }
           }
-          if (q_base) {
-            // head_mesh.py:39-43 (z translation is zero)
-            srow[0] = make_float4(qprev[0], qprev[1], qprev[2], qprev[3]);
-            srow[1] = make_float4(qprev[4], qprev[5], qprev[6], qprev[7]);
-            if (pc == 2) {
-              float qv[16];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                qv[2 * i] = ((x[3 * i] * sc + tx) + 1.0f) * hs;
-                qv[2 * i + 1] = ((x[3 * i + 1] * sc + ty) + 1.0f) * hs;
+          if constexpr (kProf) { const unsigned t = clock(); ec2 += t - et0; et0 = t; }
+          const int col0 = col_t + q * kDecPassCols;
+          const int ncols = nv3 - col0;              // valid floats from this pass's first one to the end of the row
+          if (ncols > 0) {
+            // no carry only at the start of the unit's column range; a tail only at its end or at the end of the row
+            const bool first = q == 0 && half == 0 && n == n0;
+            const bool last = (q == kDecPasses - 1 && half == 1 && n == n1 - 1) || ncols == kDecPassCols;
+            if (v_row) {
+              if (row_ok) {
+                if (ncols >= kDecPassCols) dec_store<24>(v_row + col0, c_v, vcar, x, first, last);
+                else dec_store_edge<24>(v_row + col0, c_v, vcar, x, first, ncols);
               }
 #pragma unroll
-              for (int j = 0; j < 4; ++j) srow[2 + j] = make_float4(qv[4 * j], qv[4 * j + 1], qv[4 * j + 2], qv[4 * j + 3]);
+              for (int j = 0; j < 8; ++j) vcar[j] = x[16 + j];
+            }
+            if constexpr (kProj) if (q_row) {
+              // head_mesh.py:39-43 (z translation is zero)
+              const int vfirst = col0 / 3;
+              if (pc == 2) {
+                float qv[16];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) qprev[j] = qv[8 + j];
-            } else {
-              float qv[24];
+                for (int i = 0; i < 8; ++i) {
+                  qv[2 * i] = ((x[3 * i] * sc + tx) + 1.0f) * hs;
+                  qv[2 * i + 1] = ((x[3 * i + 1] * sc + ty) + 1.0f) * hs;
+                }
+                if (row_ok) {
+                  if (ncols >= kDecPassCols) dec_store<16>(q_row + vfirst * 2, c_q, qcar, qv, first, last);
+                  else dec_store_edge<16>(q_row + vfirst * 2, c_q, qcar, qv, first, (ncols / 3) * 2);
+                }
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                qv[3 * i] = ((x[3 * i] * sc + tx) + 1.0f) * hs;
-                qv[3 * i + 1] = ((x[3 * i + 1] * sc + ty) + 1.0f) * hs;
-                qv[3 * i + 2] = ((x[3 * i + 2] * sc + 0.0f) + 1.0f) * hs;
+                for (int j = 0; j < 8; ++j) qcar[j] = qv[8 + j];
+              } else {
+                float qv[24];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  qv[3 * i] = ((x[3 * i] * sc + tx) + 1.0f) * hs;
+                  qv[3 * i + 1] = ((x[3 * i + 1] * sc + ty) + 1.0f) * hs;
+                  qv[3 * i + 2] = ((x[3 * i + 2] * sc + 0.0f) + 1.0f) * hs;
+                }
+                if (row_ok) {
+                  if (ncols >= kDecPassCols) dec_store<24>(q_row + col0, c_q, qcar, qv, first, last);
+                  else dec_store_edge<24>(q_row + col0, c_q, qcar, qv, first, ncols);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) qcar[j] = qv[16 + j];
               }
-#pragma unroll
-              for (int j = 0; j < 6; ++j) srow[2 + j] = make_float4(qv[4 * j], qv[4 * j + 1], qv[4 * j + 2], qv[4 * j + 3]);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) qprev[j] = qv[16 + j];
             }
-            __syncwarp();
-            const unsigned pitch = static_cast<unsigned>(p.nv * pc);
-            float* dst = q_base + vfirst * pc;
-            const int nval = (ncols / 3) * pc;
-            if (pc == 2) {
-              if (tile_full) dec_flush_aligned<16>(dst, pitch, stage, lane, (cb_q + 16u * q) & 7u, rho_q, q == 0, q == 3);
-              else dec_flush_edge<16>(dst, pitch, stage, lane, rows_left, nval);
-            } else {
-              if (tile_full) dec_flush_aligned<24>(dst, pitch, stage, lane, (cb_q + 24u * q) & 7u, rho_q, q == 0, q == 3);
-              else dec_flush_edge<24>(dst, pitch, stage, lane, rows_left, nval);
-            }
-            __syncwarp();
           }
-          if constexpr (kProf) ec3 += clock() - et0;
+          if constexpr (kProf) { ec3 += clock() - et0; et0 = clock(); }
         }
-        vb += kDecN / 3;
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1u;
       }
     }
     if constexpr (kProf) {
