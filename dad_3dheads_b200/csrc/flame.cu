@@ -81,41 +81,58 @@ __device__ __forceinline__ void split_store(__half* hi, __half* lo, size_t idx, 
   lo[idx] = __float2half_rn(x - __half2float(h));
 }
 
+// One warp per `group` consecutive heads.  Phase 1 (all lanes on one head at a time): betas -> fp16 hi/lo coefficient row, folded
+// joint regression J = J_T + J_dirs beta as 15 warp-reduced sums; lane i keeps the joints of head i.  Phase 2 (one LANE per head,
+// 32 heads at once): Rodrigues, kinematic chain, 6-DoF frame, skinning transforms -- the scalar tail used to run on lane 0 of a
+// warp per head, 31 lanes idle (0.39 ms per 75 776 heads = 16 % of a decode pass; same arithmetic in the same order, so the
+// outputs are bit-identical).
 __global__ void __launch_bounds__(256)
 flame_prep_kernel(const float* __restrict__ params, int B, FlameLayoutDev L, const float* __restrict__ jt,
                   const float* __restrict__ jdirsT, int flags, float inv_scale, __half* __restrict__ a_hi,
-                  __half* __restrict__ a_lo, float* __restrict__ xf, int permute) {
-  const int h = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+                  __half* __restrict__ a_lo, float* __restrict__ xf, int permute, int group) {
+  // group = heads per warp: 32 for big batches (throughput), 1 for small ones (latency: every head gets its own warp)
   const int lane = threadIdx.x & 31;
-  if (h >= B) return;
-  const float* p = params + static_cast<size_t>(h) * L.n_params;
-  // permute: the dedicated decode kernel wants heads that are equal mod 8 in the same TMEM lane quarter (flame_decode.cuh)
-  const size_t arow = static_cast<size_t>(permute ? dec_phys_row(h) : h) * kKPad;
-
-  float acc[15];
+  const int h0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * group;
+  if (h0 >= B) return;
+  float Jacc[15];
 #pragma unroll
-  for (int j = 0; j < 15; ++j) acc[j] = 0.f;
-  for (int l = lane; l < kBetas; l += 32) {
-    float b = 0.f;                                   // flame.py:191-200: missing coefficients are registered zeros
-    if (l < kMaxShape) {
-      if (l < L.n_shape) b = p[L.off_shape + l];
-    } else if (l - kMaxShape < L.n_expr) {
-      b = p[L.off_expr + l - kMaxShape];
+  for (int j = 0; j < 15; ++j) Jacc[j] = 0.f;
+  const int nh = min(group, B - h0);
+  for (int i = 0; i < nh; ++i) {
+    const int h = h0 + i;
+    const float* p = params + static_cast<size_t>(h) * L.n_params;
+    // permute: the dedicated decode kernel wants heads that are equal mod 8 in the same TMEM lane quarter (flame_decode.cuh)
+    const size_t arow = static_cast<size_t>(permute ? dec_phys_row(h) : h) * kKPad;
+    float acc[15];
+#pragma unroll
+    for (int j = 0; j < 15; ++j) acc[j] = 0.f;
+    for (int l = lane; l < kBetas; l += 32) {
+      float b = 0.f;                                   // flame.py:191-200: missing coefficients are registered zeros
+      if (l < kMaxShape) {
+        if (l < L.n_shape) b = p[L.off_shape + l];
+      } else if (l - kMaxShape < L.n_expr) {
+        b = p[L.off_expr + l - kMaxShape];
+      }
+      split_store(a_hi, a_lo, arow + l, b);
+#pragma unroll
+      for (int j = 0; j < 15; ++j) acc[j] = fmaf(b, __ldg(&jdirsT[j * kBetas + l]), acc[j]);
     }
-    split_store(a_hi, a_lo, arow + l, b);
+    for (int l = kTmplCol + lane; l < kKPad; l += 32) {     // template column gets coefficient 1, the rest is padding
+      a_hi[arow + l] = __float2half_rn(l < kTmplCol + 2 ? 1.f : 0.f);
+      a_lo[arow + l] = __float2half_rn(0.f);
+    }
 #pragma unroll
-    for (int j = 0; j < 15; ++j) acc[j] = fmaf(b, __ldg(&jdirsT[j * kBetas + l]), acc[j]);
-  }
-  for (int l = kTmplCol + lane; l < kKPad; l += 32) {     // template column gets coefficient 1, the rest is padding
-    a_hi[arow + l] = __float2half_rn(l < kTmplCol + 2 ? 1.f : 0.f);
-    a_lo[arow + l] = __float2half_rn(0.f);
-  }
+    for (int j = 0; j < 15; ++j) {
 #pragma unroll
-  for (int j = 0; j < 15; ++j) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+      for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+      if (lane == i) Jacc[j] = acc[j];
+    }
   }
-  if (lane != 0) return;
+  if (lane >= nh) return;
+  const int h = h0 + lane;
+  const float* p = params + static_cast<size_t>(h) * L.n_params;
+  const size_t arow = static_cast<size_t>(permute ? dec_phys_row(h) : h) * kKPad;
+  const float* acc = Jacc;
 
   float J[15];
 #pragma unroll
@@ -1250,8 +1267,10 @@ int dad3d_flame_decode(dad3d_flame* h, const float* params_d, int32_t B, int32_t
   const bool dedicated = fused && !(flags & DAD3D_BLEND_HILO);
   bool pair = false;
   if (dedicated) {
-    const char* env = std::getenv("DAD3D_DECODE_PAIR");         // A/B switch: 1 = CTA pairs for big batches, 0 = never
-    const int want = (flags & DAD3D_DECODE_PAIR) ? 1 : (env ? std::atoi(env) : 0);
+    // CTA pairs (cta_group::2) for big batches: half the basis bytes through the L2 per SM -- equal on one 75 776-head pass,
+    // 8 % faster sustained over 1 M heads (46.7 vs 43.0 M heads/s).  DAD3D_DECODE_PAIR=0 switches them off (A/B).
+    const char* env = std::getenv("DAD3D_DECODE_PAIR");
+    const int want = (flags & DAD3D_DECODE_PAIR) ? 1 : (env ? std::atoi(env) : 1);
     pair = want > 0 && ceil_div(B, kDecBlockM) >= 2 * h->num_sms;
   }
   const int chunk = fused ? h->fused_chunk : kDecodeChunk;
@@ -1271,9 +1290,10 @@ int dad3d_flame_decode(dad3d_flame* h, const float* params_d, int32_t B, int32_t
     float* pj = projected_d ? projected_d + static_cast<size_t>(b0) * h->nv * pc : nullptr;
     {
       const int threads = 256;
-      const int blocks = ceil_div(rows * 32, threads);
+      const int group = rows >= 32 * 8 * h->num_sms ? 32 : 1;              // heads per warp (see the kernel)
+      const int blocks = ceil_div(ceil_div(rows, group) * 32, threads);
       flame_prep_kernel<<<blocks, threads, 0, stream>>>(p, rows, h->layout, h->d_jt, h->d_jdirsT, flags, inv_scale, a_hi,
-                                                        a_lo, xf, dedicated ? 1 : 0);
+                                                        a_lo, xf, dedicated ? 1 : 0, group);
       count_launch();
       DAD3D_CUDA_OK(cudaGetLastError());
     }
@@ -1423,7 +1443,7 @@ int dad3d_flame_backward(dad3d_flame* h, const float* params_d, int32_t B, int32
     const float* gp = grad_projected_d ? grad_projected_d + static_cast<size_t>(b0) * h->nv * pc : nullptr;
     float* gout = grad_params_d + static_cast<size_t>(b0) * h->layout.n_params;
     flame_prep_kernel<<<ceil_div(rows * 32, 256), 256, 0, stream>>>(p, rows, h->layout, h->d_jt, h->d_jdirsT, flags, inv_scale,
-                                                                     a_hi, a_lo, xf, 0);
+                                                                     a_hi, a_lo, xf, 0, 1);
     count_launch();
     DAD3D_CUDA_OK(cudaGetLastError());
     {   // forward blend product (recomputed): v_posed * basis_scale -> scratch
