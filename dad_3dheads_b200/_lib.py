@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdad3d.so")
+LIB_PATH = os.environ.get("DAD3D_LIB_PATH") or os.path.join(_HERE, "libdad3d.so")   # override: A/B runs of two builds
 
 DAD3D_ZERO_ROT = 1
 DAD3D_ZERO_JAW = 2

@@ -432,8 +432,8 @@ flame_decode_kernel(const __grid_constant__ CUtensorMap map_a,     // coefficien
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) {
-            if constexpr (kPair) ptx::mbar_arrive_cluster(tempty_remote);
-            else ptx::mbar_arrive(&tempty_bar[acc]);
+            if constexpr (kPair) ptx::mbar_arrive_cluster_relaxed(tempty_remote);
+            else ptx::mbar_arrive_relaxed(&tempty_bar[acc]);
           }
           continue;
         }
@@ -504,8 +504,8 @@ flame_decode_kernel(const __grid_constant__ CUtensorMap map_a,     // coefficien
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-              if constexpr (kPair) ptx::mbar_arrive_cluster(tempty_remote);
-              else ptx::mbar_arrive(&tempty_bar[acc]);
+              if constexpr (kPair) ptx::mbar_arrive_cluster_relaxed(tempty_remote);
+              else ptx::mbar_arrive_relaxed(&tempty_bar[acc]);
             }
           }
           if constexpr (kProf) { const unsigned t = clock(); ec2 += t - et0; et0 = t; }

@@ -166,6 +166,15 @@ __device__ __forceinline__ uint32_t mapa_u32(const void* local, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(local)), "r"(rank));
   return r;
 }
+// Relaxed arrives: the default (.release) makes the arriving thread wait for its earlier GLOBAL stores first (MEMBAR.ALL.CTA /
+// .GPU in SASS).  Right for handing data over, wrong for an epilogue warp that only says "I have read the accumulator" -- there
+// the completed tcgen05.wait::ld is the ordering that matters and the stores may stay in flight.
+__device__ __forceinline__ void mbar_arrive_relaxed(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
