@@ -45,7 +45,7 @@ def test_simt_blend_matches_oracle(head_mesh, oracle64, cuda_device):
     assert _rel(pj, oracle64.reprojected_vertices(p)) < 2e-6
 
 
-@pytest.mark.parametrize("B", [1, 2, 3, 4, 64, 127, 128, 129, 512])
+@pytest.mark.parametrize("B", [1, 2, 3, 4, 5, 64, 127, 128, 129, 255, 257, 261, 512])   # incl. the edges of the 256-head row permutation blocks
 @pytest.mark.parametrize("hilo", [False, True])
 def test_decode_matches_oracle(head_mesh, oracle64, cuda_device, B, hilo):
     p = sample_params(B, seed=100 + B)
