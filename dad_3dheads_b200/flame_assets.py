@@ -3,7 +3,7 @@
 
 ``flame.pkl`` is a python-2 era pickle that references ``chumpy.ch.Ch`` and ``scipy.sparse.csc.csc_matrix``; chumpy is not a
 dependency of this package, so a restricted unpickler substitutes a stub for it (payload attribute ``x``) and refuses every
-class outside numpy / scipy.sparse / builtins.  ``load_flame_pickle`` returns the same fp32 arrays the packed
+global outside a short whitelist (numpy array reconstruction, scipy csc_matrix, plain containers).  ``load_flame_pickle`` returns the same fp32 arrays the packed
 ``assets/flame_static.npz`` holds (tests/test_oracle_pinned.py checks the two bit for bit against the reference's own
 FLAMELayer buffers), so ``FLAMELayer(consts, flame_path=".../flame.pkl")`` works at run time exactly like the reference's.
 """
@@ -24,16 +24,32 @@ class _ChStub:
 
 
 class _RestrictedUnpickler(pickle.Unpickler):
-    _ALLOWED_PREFIX = ("numpy", "scipy.sparse", "collections", "builtins", "copyreg")
+    """Whitelist of exactly the globals FLAME-style pickles need (flame.pkl / generic_model.pkl of the reference:
+    numpy.dtype, numpy.ndarray, numpy.core.multiarray._reconstruct, scipy.sparse csc_matrix, chumpy.ch.Ch, builtins set) plus
+    the inert container / scalar types protocol-2 pickles of numpy data may name.  A module PREFIX is not enough: "builtins"
+    also holds eval / exec / __import__, "numpy" holds load / fromfile -- everything else is refused."""
+
+    _ALLOWED = {
+        "builtins": {"set", "frozenset", "list", "dict", "tuple", "object", "slice", "range", "complex", "int", "float", "bool",
+                     "str", "bytes", "bytearray"},
+        "collections": {"OrderedDict", "defaultdict"},
+        "copyreg": {"_reconstructor"},
+        "_codecs": {"encode"},                      # how protocol-2 pickles written by python 3 carry numpy's raw bytes
+        "numpy": {"dtype", "ndarray"},
+        "numpy.core.multiarray": {"_reconstruct", "scalar"},
+        "numpy._core.multiarray": {"_reconstruct", "scalar"},
+        "numpy.core.numeric": {"_frombuffer"},
+        "numpy._core.numeric": {"_frombuffer"},
+    }
 
     def find_class(self, module, name):
-        if module.startswith("chumpy"):
+        if module in ("chumpy.ch", "chumpy") and name == "Ch":
             return _ChStub
         if module in ("scipy.sparse.csc", "scipy.sparse._csc") and name == "csc_matrix":
             import scipy.sparse
             return scipy.sparse.csc_matrix
         module = {"__builtin__": "builtins", "copy_reg": "copyreg"}.get(module, module)
-        if not module.startswith(self._ALLOWED_PREFIX):
+        if name not in self._ALLOWED.get(module, ()):
             raise pickle.UnpicklingError(f"refusing to unpickle {module}.{name}")
         return super().find_class(module, name)
 
