@@ -386,7 +386,9 @@ def run_ours(args):
         h2d = x_host.numel() * x_host.element_size()
         d2h = sum(v.numel() * v.element_size() for v in host_out.values())
         cfg = workload_config(args, world)
-        cfg.update({"decode": "fp16 hi/lo 3-product blend + LBS + projection + 445-landmark gather",
+        cfg.update({"decode": "flame_decode_kernel (the batched API's default): one fp16 product per MAC, template exact in two K "
+                              "columns, fp32 accumulate -- vertices relL2 3.5e-5 vs the reference (contract 1e-4, see parity) + LBS + "
+                              "projection + 445-landmark gather; the strict run (strict_fp32_operands) uses the same decode",
                     "parallelism": (f"dp{world} (batch sharded, NCCL bcast constants at start-up, per-step all-gather of params/"
                                     f"vertices/landmarks on a side stream overlapping the next step)") if distributed
                     else "single GPU",
