@@ -52,8 +52,9 @@ typedef struct dad3d_flame_layout {
                                    relL2 2e-7 vs fp64) through the generic tile engine.  DEFAULT (flag absent): ONE fp16 product
                                    (11-bit operand mantissa like TF32, template exact to 22 bits; vertices relL2 1.5e-5, inside
                                    the 1e-4 contract) in the dedicated A-stationary decode kernel (csrc/flame_decode.cuh) */
-#define DAD3D_DECODE_PAIR 128   /* A/B aid: run the dedicated decode kernel as CTA pairs (cta_group::2) when the batch has at
-                                   least two row tiles per SM (also: environment DAD3D_DECODE_PAIR=1) */
+#define DAD3D_DECODE_PAIR 128   /* run the dedicated decode kernel as CTA pairs (cta_group::2) when the batch has at least two row
+                                   tiles per SM.  Pairs are the default there since round 2 (environment DAD3D_DECODE_PAIR=0
+                                   switches them off for A/B runs); the flag forces them regardless of the environment */
 #define DAD3D_BLEND_SIMT 8      /* verification aid: blend-shape product on CUDA cores in fp32 (slow) */
 #define DAD3D_DECODE_UNFUSED 16 /* A/B aid: tensor-core blend product to a v_posed scratch + separate skinning kernel
                                    (default: skinning / rotation / projection fused into the GEMM epilogue) */
