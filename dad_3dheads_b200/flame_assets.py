@@ -92,30 +92,27 @@ def load_flame_pickle(path: str) -> Dict[str, np.ndarray]:
 
 
 def load_indices_from_npy(filepath: str):
-    """model_training/utils.py:99-105: an .npy holding an ordered dict of index lists -> one flat list."""
-    data = np.load(filepath, allow_pickle=True)[()]
-    lst = []
-    for value in data.values():
-        lst += list(value)
-    return lst
+    """model_training/utils.py:99-105: an .npy holding an (ordered) dict of index lists -> their concatenation, in dict order."""
+    groups = np.load(filepath, allow_pickle=True).item()
+    return [i for indices in groups.values() for i in indices]
 
 
 def get_list_of_npy_files(config: Dict) -> list:
-    """model_training/utils.py:81-96: the .npy files of a key-point subset folder, minus ``2d_keys_exclude`` (default cheeks)."""
-    subset_path = str(config.get("2d_subset_path"))
-    subset = config.get("2d_keys", "all")
-    exclude = config.get("2d_keys_exclude", "cheeks")
-    files = os.listdir(subset_path)
-    if isinstance(subset, str) and subset == "all":
-        subset = [x.split(".")[0] for x in files]
-        if exclude is not None:
-            if isinstance(exclude, str):
-                exclude = [exclude]
-            for feature in exclude:
-                if feature in subset:
-                    subset.remove(feature)
-        subset = [os.path.join(subset_path, x + ".npy") for x in subset]
-    return subset
+    """model_training/utils.py:81-96.  ``2d_keys == "all"`` (the default): every file of ``2d_subset_path``, named by its stem,
+    except the stems listed in ``2d_keys_exclude`` (a name or a list; default "cheeks"; None keeps everything), returned as
+    ``<folder>/<stem>.npy``.  Any other ``2d_keys`` value is handed back unchanged, as the reference does."""
+    folder = str(config.get("2d_subset_path"))
+    keys = config.get("2d_keys", "all")
+    entries = os.listdir(folder)                          # (the reference lists the folder before looking at the keys, too)
+    if not (isinstance(keys, str) and keys == "all"):
+        return keys
+    dropped = config.get("2d_keys_exclude", "cheeks")
+    dropped = [] if dropped is None else [dropped] if isinstance(dropped, str) else list(dropped)
+    stems = [name.split(".")[0] for name in entries]
+    for stem in dropped:
+        if stem in stems:
+            stems.remove(stem)                            # first occurrence only, like list.remove in the reference
+    return [os.path.join(folder, stem + ".npy") for stem in stems]
 
 
 def load_static(path: Optional[str], default_npz: str) -> Dict[str, np.ndarray]:
