@@ -93,7 +93,7 @@ def load_flame_pickle(path: str) -> Dict[str, np.ndarray]:
 
 def load_indices_from_npy(filepath: str):
     """model_training/utils.py:99-105: an .npy holding an (ordered) dict of index lists -> their concatenation, in dict order."""
-    groups = np.load(filepath, allow_pickle=True).item()
+    groups = np.load(filepath, allow_pickle=True)[()]          # 0-d object array -> the dict it wraps
     return [i for indices in groups.values() for i in indices]
 
 
