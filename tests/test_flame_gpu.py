@@ -178,9 +178,19 @@ def test_chunk_boundary_and_batch_independence(head_mesh, cuda_device):
     vb, pb = dec.decode(p[:n], want_vertices=True, want_projected=True, cluster=True)
     assert torch.equal(va, vb) and torch.equal(pa, pb)
     del va, pa, vb, pb
-    # opt-in variant of the default kernel: CTA pairs (cta_group::2) for batches with >= 2 row tiles per SM -- same arithmetic
+    # CTA pairs (cta_group::2; the default for batches with >= 2 row tiles per SM) against single CTAs (DAD3D_DECODE_PAIR=0,
+    # read at every call) -- same arithmetic
+    import os
     n = props.multi_processor_count * 128 * 2 + 77
-    va, pa = dec.decode(p[:n], want_vertices=True, want_projected=True)
+    old_env = os.environ.get("DAD3D_DECODE_PAIR")
+    os.environ["DAD3D_DECODE_PAIR"] = "0"
+    try:
+        va, pa = dec.decode(p[:n], want_vertices=True, want_projected=True)
+    finally:
+        if old_env is None:
+            del os.environ["DAD3D_DECODE_PAIR"]
+        else:
+            os.environ["DAD3D_DECODE_PAIR"] = old_env
     vb, pb = dec.decode(p[:n], want_vertices=True, want_projected=True, pair=True)
     assert torch.equal(va, vb) and torch.equal(pa, pb)
 
